@@ -1,0 +1,148 @@
+/*
+ * nns_b200.h -- C ABI of the B200-native Navier-Stokes step library (libnns_b200.so).
+ *
+ * The reference (mhw32/neural-navier-stokes) is pure Python and has no FFI layer; this ABI
+ * is the boundary a maintainer would bind UNDER the reference's solver classes.  Each entry
+ * point names the reference code it replaces (paths relative to the reference root).
+ * INTEGRATION.md shows the ctypes stub that goes into the reference.
+ *
+ * Conventions
+ *   - All fields are C-contiguous float64 [batch][nx][ny], index [i][j], j fastest; side ->
+ *     index map as in src/boundary.py:39-46 (left=A[0,:], right=A[-1,:], bottom=A[:,0],
+ *     top=A[:,-1]).
+ *   - `*_run`, `*_step` and stage entry points take DEVICE pointers (caller-owned), are
+ *     asynchronous and ordered on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream).  `*_host` entry points take HOST pointers and are synchronous; the
+ *     host<->device copies happen inside the call.
+ *   - Every function returns 0 on success or a negative nns_status; the message is
+ *     available from nns_last_error() (thread-local).  No C++ exception crosses the ABI.
+ *   - There is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef NNS_B200_H
+#define NNS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NNS_ABI_VERSION 1
+#define NNS_MAX_BC 8 /* per field */
+
+typedef enum nns_status {
+    NNS_OK = 0,
+    NNS_ERR_INVALID = -1,     /* bad argument (mirrors the reference's AssertionError / Exception) */
+    NNS_ERR_CUDA = -2,        /* CUDA runtime failure, message carries cudaGetErrorString */
+    NNS_ERR_UNSUPPORTED = -3, /* e.g. spectral Neumann BC (src/chorin_spectral/simulate.py:221) */
+    NNS_ERR_NONFINITE = -4,   /* overflow/NaN seen; the reference raises (warnings are errors, chorin_fd:3) */
+    NNS_ERR_NOMEM = -5
+} nns_status;
+
+enum { NNS_SOLVER_CHORIN_FD = 0, NNS_SOLVER_DIRECT_FD = 1, NNS_SOLVER_CHORIN_SPECTRAL = 2 };
+enum { NNS_METHOD_EXPLICIT = 0, NNS_METHOD_SEMI_IMPLICIT = 1 };
+enum { NNS_FIELD_U = 0, NNS_FIELD_V = 1, NNS_FIELD_P = 2 };
+enum { NNS_SIDE_LEFT = 0, NNS_SIDE_RIGHT = 1, NNS_SIDE_BOTTOM = 2, NNS_SIDE_TOP = 3 };
+enum { NNS_BC_DIRICHLET = 0, NNS_BC_NEUMANN = 1 };
+
+/* One boundary condition; replaces a src/boundary.py BoundaryCondition object
+ * (boundary.py:14-23).  The ORDER of the entries of one field is the order of the
+ * reference's u_bc / v_bc / p_bc lists and is preserved (later entries overwrite corners). */
+typedef struct nns_bc {
+    int32_t field; /* NNS_FIELD_* */
+    int32_t side;  /* NNS_SIDE_*  */
+    int32_t type;  /* NNS_BC_*    */
+    int32_t reserved;
+    double value;
+} nns_bc;
+
+/* Constructor arguments of the reference's NavierStokesSystem
+ * (src/chorin_fd/simulate.py:51-61, src/direct_fd/simulate.py:46-54,
+ *  src/chorin_spectral/simulate.py:41-52) plus the ensemble batch. */
+typedef struct nns_params {
+    int32_t solver; /* NNS_SOLVER_* */
+    int32_t method; /* NNS_METHOD_* (chorin_fd only) */
+    int32_t nx, ny;
+    int32_t batch;  /* independent simulations advanced together (1 = the reference's case) */
+    int32_t nit;
+    double dt, rho, nu, beta;
+    double tol;     /* SOR exit tolerance; <= 0 selects the reference's 5e-6 (chorin_fd:183) */
+    int32_t device; /* CUDA ordinal, -1 = current device */
+    int32_t flags;  /* NNS_FLAG_* */
+} nns_params;
+
+#define NNS_FLAG_CHECK_FINITE 1 /* count non-finite outputs; *_host calls then return NNS_ERR_NONFINITE */
+
+typedef struct nns_handle nns_handle;
+
+int32_t nns_abi_version(void);
+const char *nns_last_error(void);
+
+/* Create / destroy a solver instance (device workspace is allocated here, once).
+ * nu_per_member: host array [batch] or NULL (use params->nu).
+ * bc_value_per_member: host array [batch][n_bcs] overriding bcs[k].value per member, or NULL. */
+int32_t nns_create(const nns_params *params, const nns_bc *bcs, int32_t n_bcs, const double *nu_per_member,
+                   const double *bc_value_per_member, nns_handle **out);
+int32_t nns_destroy(nns_handle *h);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t nns_launch_count(const nns_handle *h);
+/* Non-finite values seen since creation (needs NNS_FLAG_CHECK_FINITE); synchronises the stream. */
+int32_t nns_nonfinite_count(nns_handle *h, int64_t *count);
+
+/* Sequential BC application on a device field [batch][nx][ny], in list order
+ * (src/boundary.py:34-86; NavierStokesSystem._init_variables, chorin_fd/simulate.py:236-249).
+ * Uses the handle's BC list of `field`. */
+int32_t nns_apply_bc(nns_handle *h, int32_t field, double *a, void *stream);
+
+/* ---- chorin_fd (src/chorin_fd/simulate.py) --------------------------------------- */
+
+/* One time step, replaces NavierStokesSystem.step (chorin_fd/simulate.py:212-234):
+ * predictor (:63-91 or :93-167) + u/v BCs (:221-225) + SOR pressure (:169-202, exact
+ * lexicographic order, at most nit-1 sweeps, early exit at max|dp| <= tol) + p BCs
+ * (:230-231) + projection (:204-210).  Reads u,v,u1,v1; writes u_out,v_out (must not
+ * alias the inputs); p is updated in place.  sweeps_out: device int32 [batch] or NULL. */
+int32_t nns_chorin_fd_step(nns_handle *h, const double *u, const double *v, const double *u1,
+                           const double *v1, double *p, double *u_out, double *v_out, int32_t *sweeps_out,
+                           void *stream);
+
+/* nsteps time steps, replaces the loop of NavierStokesSystem.simulate (:258-265).  On
+ * return u,v hold step n, u1,v1 step n-1, p step n.  traj_*: device [batch][nsteps][nx][ny]
+ * or NULL (the reference keeps every step, :263-265).  sweeps_out: device int32
+ * [nsteps][batch] or NULL. */
+int32_t nns_chorin_fd_run(nns_handle *h, double *u, double *v, double *u1, double *v1, double *p,
+                          int32_t nsteps, double *traj_u, double *traj_v, double *traj_p,
+                          int32_t *sweeps_out, void *stream);
+
+/* Same with HOST buffers (synchronous; copies inside).  This is the call the reference's
+ * simulate() would make.  traj_* / sweeps_out may be NULL. */
+int32_t nns_chorin_fd_run_host(nns_handle *h, double *u, double *v, double *u1, double *v1, double *p,
+                               int32_t nsteps, double *traj_u, double *traj_v, double *traj_p,
+                               int32_t *sweeps_out);
+
+/* Stage entry points for unit parity (device pointers):
+ *   predictor: _explicit/_semi_implicit_predictor_step + u_bc/v_bc   -> ui, vi
+ *   pressure : _get_pressure (no p BCs), p in place                  -> p, sweeps_out[batch]
+ *   correct  : p_bc + _correction_step, p in place                   -> u_out, v_out        */
+int32_t nns_chorin_fd_predictor(nns_handle *h, const double *u, const double *v, const double *u1,
+                                const double *v1, double *ui, double *vi, void *stream);
+int32_t nns_chorin_fd_pressure(nns_handle *h, const double *ui, const double *vi, double *p,
+                               int32_t *sweeps_out, void *stream);
+int32_t nns_chorin_fd_correct(nns_handle *h, const double *ui, const double *vi, double *p, double *u_out,
+                              double *v_out, void *stream);
+
+/* ---- direct_fd (src/direct_fd/simulate.py) ---------------------------------------- */
+
+/* nsteps of NavierStokesSystem.step (direct_fd/simulate.py:90-127): RHS b (:56-66), exactly
+ * nit Jacobi sweeps with p BCs after every sweep (:68-88), upwind/central update (:98-118),
+ * u/v BCs (:121-125).  u, v, p are advanced IN PLACE (as the reference does, :132).
+ * traj_*: device [batch][nsteps][nx][ny] or NULL. */
+int32_t nns_direct_fd_run(nns_handle *h, double *u, double *v, double *p, int32_t nsteps, double *traj_u,
+                          double *traj_v, double *traj_p, void *stream);
+int32_t nns_direct_fd_run_host(nns_handle *h, double *u, double *v, double *p, int32_t nsteps,
+                               double *traj_u, double *traj_v, double *traj_p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNS_B200_H */

@@ -1,0 +1,322 @@
+// api.cu -- extern "C" entry points of libnns_b200 (see include/nns_b200.h).
+#include <stdarg.h>
+#include <math.h>
+
+#include <new>
+#include <vector>
+
+#include "nns_common.cuh"
+
+namespace nns {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// chorin_fd_chip.cu
+struct ChipArgs;
+int chorin_chip_run(nns_handle *h, double *bufU[3], double *bufV[3], double *p, int nsteps, int nsteps_total,
+                    int step0, int phases, int fixup, double *tu, double *tv, double *tp, int32_t *sweeps,
+                    cudaStream_t st);
+bool chorin_chip_fits(const nns_handle *h);
+// chorin_fd_tiled.cu
+int chorin_tiled_run(nns_handle *h, double *bufU[3], double *bufV[3], double *p, int nsteps, int nsteps_total,
+                     int step0, int phases, int fixup, double *tu, double *tv, double *tp, int32_t *sweeps,
+                     cudaStream_t st);
+// direct_fd.cu
+int direct_run(nns_handle *h, double *u, double *v, double *p, int nsteps, double *tu, double *tv, double *tp,
+               cudaStream_t st);
+int launch_apply_bc(nns_handle *h, int field, double *a, cudaStream_t st);
+
+static int ensure_scratch(nns_handle *h, int k) {
+    if (h->d_scratch[k]) return NNS_OK;
+    NNS_CUDA(cudaMalloc(&h->d_scratch[k], sizeof(double) * (size_t)h->g.nx * h->g.ny * h->g.batch));
+    return NNS_OK;
+}
+
+static int chorin_dispatch(nns_handle *h, double *bufU[3], double *bufV[3], double *p, int nsteps,
+                           int nsteps_total, int step0, int phases, int fixup, double *tu, double *tv,
+                           double *tp, int32_t *sweeps, cudaStream_t st) {
+    if (chorin_chip_fits(h))
+        return chorin_chip_run(h, bufU, bufV, p, nsteps, nsteps_total, step0, phases, fixup, tu, tv, tp, sweeps, st);
+    return chorin_tiled_run(h, bufU, bufV, p, nsteps, nsteps_total, step0, phases, fixup, tu, tv, tp, sweeps, st);
+}
+
+}  // namespace nns
+
+using namespace nns;
+
+#define NNS_CHECK_HANDLE(h, solver_)                                           \
+    do {                                                                       \
+        if (!(h)) { set_error("null handle"); return NNS_ERR_INVALID; }        \
+        if ((h)->params.solver != (solver_)) {                                 \
+            set_error("handle was created for solver %d", (h)->params.solver); \
+            return NNS_ERR_INVALID;                                            \
+        }                                                                      \
+        NNS_CUDA(cudaSetDevice((h)->device));                                  \
+    } while (0)
+
+extern "C" {
+
+int32_t nns_abi_version(void) { return NNS_ABI_VERSION; }
+const char *nns_last_error(void) { return g_err; }
+
+int32_t nns_create(const nns_params *P, const nns_bc *bcs, int32_t n_bcs, const double *nu_b,
+                   const double *bcval_b, nns_handle **out) {
+    if (!P || !out || (n_bcs > 0 && !bcs)) { set_error("nns_create: null argument"); return NNS_ERR_INVALID; }
+    *out = nullptr;
+    if (P->nx < 3 || P->ny < 3 || P->batch < 1 || P->nit < 0) {
+        set_error("nns_create: need nx,ny >= 3, batch >= 1, nit >= 0 (got %d,%d,%d,%d)", P->nx, P->ny, P->batch, P->nit);
+        return NNS_ERR_INVALID;
+    }
+    if (P->solver < NNS_SOLVER_CHORIN_FD || P->solver > NNS_SOLVER_CHORIN_SPECTRAL) {
+        set_error("nns_create: unknown solver %d", P->solver);
+        return NNS_ERR_INVALID;
+    }
+    if (P->solver == NNS_SOLVER_CHORIN_FD && P->method != NNS_METHOD_EXPLICIT && P->method != NNS_METHOD_SEMI_IMPLICIT) {
+        set_error("method not recognized: %d", P->method);   // chorin_fd/simulate.py:60,218
+        return NNS_ERR_INVALID;
+    }
+    if (P->solver == NNS_SOLVER_CHORIN_FD && P->method == NNS_METHOD_SEMI_IMPLICIT && P->nx != P->ny) {
+        set_error("semi_implicit needs nx == ny (the reference solves B along axis 0, chorin_fd/simulate.py:159)");
+        return NNS_ERR_INVALID;
+    }
+    if (!(P->dt > 0) || !(P->rho != 0)) { set_error("nns_create: dt must be > 0 and rho != 0"); return NNS_ERR_INVALID; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device: libnns_b200 has no CPU fallback");
+        return NNS_ERR_CUDA;
+    }
+    nns_handle *h = new (std::nothrow) nns_handle();
+    if (!h) { set_error("out of host memory"); return NNS_ERR_NOMEM; }
+    memset(h, 0, sizeof(*h));
+    h->params = *P;
+    if (P->device >= 0) h->device = P->device;
+    else NNS_CUDA(cudaGetDevice(&h->device));
+    NNS_CUDA(cudaSetDevice(h->device));
+    NNS_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device));
+    NNS_CUDA(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    Geometry &g = h->g;
+    g.nx = P->nx; g.ny = P->ny; g.batch = P->batch; g.nit = P->nit; g.method = P->method;
+    g.dt = P->dt; g.rho = P->rho; g.nu = P->nu; g.beta = P->beta;
+    g.tol = P->tol > 0 ? P->tol : 5e-6;
+    if (P->solver == NNS_SOLVER_CHORIN_SPECTRAL) { g.dx = 2.0 / P->nx; g.dy = 2.0 / P->ny; }   // chorin_spectral:48
+    else { g.dx = 2.0 / (P->nx - 1); g.dy = 2.0 / (P->ny - 1); }                               // chorin_fd:58
+    h->n_bcs = n_bcs;
+    for (int k = 0; k < n_bcs; ++k) {
+        const nns_bc &b = bcs[k];
+        if (b.field < 0 || b.field > 2 || b.side < 0 || b.side > 3 || b.type < 0 || b.type > 1) {
+            set_error("nns_create: bad boundary condition #%d (field %d side %d type %d)", k, b.field, b.side, b.type);
+            delete h;
+            return NNS_ERR_INVALID;
+        }
+        BcList &L = h->bc[b.field];
+        if (L.n >= NNS_MAX_BC) { set_error("more than %d boundary conditions on one field", NNS_MAX_BC); delete h; return NNS_ERR_INVALID; }
+        L.side[L.n] = b.side; L.type[L.n] = b.type; L.value[L.n] = b.value; L.slot[L.n] = k;
+        L.n++;
+    }
+    if (nu_b) {
+        NNS_CUDA(cudaMalloc(&h->d_nu, sizeof(double) * g.batch));
+        NNS_CUDA(cudaMemcpy(h->d_nu, nu_b, sizeof(double) * g.batch, cudaMemcpyHostToDevice));
+    }
+    if (bcval_b && n_bcs > 0) {
+        NNS_CUDA(cudaMalloc(&h->d_bcval, sizeof(double) * (size_t)g.batch * n_bcs));
+        NNS_CUDA(cudaMemcpy(h->d_bcval, bcval_b, sizeof(double) * (size_t)g.batch * n_bcs, cudaMemcpyHostToDevice));
+    }
+    NNS_CUDA(cudaMalloc(&h->d_nonfinite, sizeof(unsigned long long)));
+    NNS_CUDA(cudaMemset(h->d_nonfinite, 0, sizeof(unsigned long long)));
+    NNS_CUDA(cudaMalloc(&h->d_sweeps, sizeof(int32_t) * g.batch));
+    *out = h;
+    return NNS_OK;
+}
+
+int32_t nns_destroy(nns_handle *h) {
+    if (!h) return NNS_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_nu); cudaFree(h->d_bcval); cudaFree(h->d_cprime); cudaFree(h->d_b); cudaFree(h->d_p2);
+    cudaFree(h->d_sweeps); cudaFree(h->d_nonfinite);
+    for (int k = 0; k < 4; ++k) cudaFree(h->d_scratch[k]);
+    delete h;
+    return NNS_OK;
+}
+
+int64_t nns_launch_count(const nns_handle *h) { return h ? h->launches : 0; }
+
+int32_t nns_nonfinite_count(nns_handle *h, int64_t *count) {
+    if (!h || !count) { set_error("null argument"); return NNS_ERR_INVALID; }
+    NNS_CUDA(cudaSetDevice(h->device));
+    unsigned long long c = 0;
+    NNS_CUDA(cudaMemcpy(&c, h->d_nonfinite, sizeof(c), cudaMemcpyDeviceToHost));
+    *count = (int64_t)c;
+    return NNS_OK;
+}
+
+int32_t nns_apply_bc(nns_handle *h, int32_t field, double *a, void *stream) {
+    if (!h || !a || field < 0 || field > 2) { set_error("nns_apply_bc: bad argument"); return NNS_ERR_INVALID; }
+    NNS_CUDA(cudaSetDevice(h->device));
+    return launch_apply_bc(h, field, a, (cudaStream_t)stream);
+}
+
+// ---- chorin_fd -------------------------------------------------------------------------------
+
+int32_t nns_chorin_fd_step(nns_handle *h, const double *u, const double *v, const double *u1, const double *v1,
+                           double *p, double *u_out, double *v_out, int32_t *sweeps_out, void *stream) {
+    NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_FD);
+    if (!u || !v || !u1 || !v1 || !p || !u_out || !v_out) { set_error("nns_chorin_fd_step: null field"); return NNS_ERR_INVALID; }
+    if (u_out == u || u_out == u1 || v_out == v || v_out == v1) { set_error("nns_chorin_fd_step: outputs alias inputs"); return NNS_ERR_INVALID; }
+    double *bu[3] = {const_cast<double *>(u), const_cast<double *>(u1), u_out};
+    double *bv[3] = {const_cast<double *>(v), const_cast<double *>(v1), v_out};
+    return chorin_dispatch(h, bu, bv, p, 1, 1, 0, 7, 0, nullptr, nullptr, nullptr, sweeps_out, (cudaStream_t)stream);
+}
+
+int32_t nns_chorin_fd_run(nns_handle *h, double *u, double *v, double *u1, double *v1, double *p, int32_t nsteps,
+                          double *tu, double *tv, double *tp, int32_t *sweeps_out, void *stream) {
+    NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_FD);
+    if (!u || !v || !u1 || !v1 || !p || nsteps < 0) { set_error("nns_chorin_fd_run: bad argument"); return NNS_ERR_INVALID; }
+    if (nsteps == 0) return NNS_OK;
+    int rc;
+    if ((rc = ensure_scratch(h, 0)) || (rc = ensure_scratch(h, 1))) return rc;
+    double *bu[3] = {u, u1, h->d_scratch[0]};
+    double *bv[3] = {v, v1, h->d_scratch[1]};
+    return chorin_dispatch(h, bu, bv, p, nsteps, nsteps, 0, 7, 1, tu, tv, tp, sweeps_out, (cudaStream_t)stream);
+}
+
+int32_t nns_chorin_fd_predictor(nns_handle *h, const double *u, const double *v, const double *u1,
+                                const double *v1, double *ui, double *vi, void *stream) {
+    NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_FD);
+    if (!u || !v || !u1 || !v1 || !ui || !vi) { set_error("nns_chorin_fd_predictor: null field"); return NNS_ERR_INVALID; }
+    double *bu[3] = {const_cast<double *>(u), const_cast<double *>(u1), ui};
+    double *bv[3] = {const_cast<double *>(v), const_cast<double *>(v1), vi};
+    return chorin_dispatch(h, bu, bv, nullptr, 1, 1, 0, 1, 0, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int32_t nns_chorin_fd_pressure(nns_handle *h, const double *ui, const double *vi, double *p, int32_t *sweeps_out,
+                               void *stream) {
+    NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_FD);
+    if (!ui || !vi || !p) { set_error("nns_chorin_fd_pressure: null field"); return NNS_ERR_INVALID; }
+    double *bu[3] = {nullptr, nullptr, const_cast<double *>(ui)};
+    double *bv[3] = {nullptr, nullptr, const_cast<double *>(vi)};
+    return chorin_dispatch(h, bu, bv, p, 1, 1, 0, 2, 0, nullptr, nullptr, nullptr, sweeps_out, (cudaStream_t)stream);
+}
+
+int32_t nns_chorin_fd_correct(nns_handle *h, const double *ui, const double *vi, double *p, double *u_out,
+                              double *v_out, void *stream) {
+    NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_FD);
+    if (!ui || !vi || !p || !u_out || !v_out) { set_error("nns_chorin_fd_correct: null field"); return NNS_ERR_INVALID; }
+    const size_t bytes = sizeof(double) * (size_t)h->g.nx * h->g.ny * h->g.batch;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (u_out != ui) NNS_CUDA(cudaMemcpyAsync(u_out, ui, bytes, cudaMemcpyDeviceToDevice, st));
+    if (v_out != vi) NNS_CUDA(cudaMemcpyAsync(v_out, vi, bytes, cudaMemcpyDeviceToDevice, st));
+    double *bu[3] = {nullptr, nullptr, u_out};
+    double *bv[3] = {nullptr, nullptr, v_out};
+    return chorin_dispatch(h, bu, bv, p, 1, 1, 0, 4, 0, nullptr, nullptr, nullptr, nullptr, st);
+}
+
+// Host-buffer helpers ------------------------------------------------------------------------
+namespace {
+struct DevBuf {
+    double *p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    int alloc(size_t bytes) { NNS_CUDA(cudaMalloc(&p, bytes)); return NNS_OK; }
+};
+}  // namespace
+
+int32_t nns_chorin_fd_run_host(nns_handle *h, double *u, double *v, double *u1, double *v1, double *p,
+                               int32_t nsteps, double *tu, double *tv, double *tp, int32_t *sweeps_out) {
+    NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_FD);
+    if (!u || !v || !u1 || !v1 || !p || nsteps < 0) { set_error("nns_chorin_fd_run_host: bad argument"); return NNS_ERR_INVALID; }
+    const size_t bytes = sizeof(double) * (size_t)h->g.nx * h->g.ny * h->g.batch;
+    DevBuf f[5], t[3];
+    int32_t *dsw = nullptr;
+    int rc;
+    double *hostf[5] = {u, v, u1, v1, p};
+    for (int k = 0; k < 5; ++k) {
+        if ((rc = f[k].alloc(bytes))) return rc;
+        NNS_CUDA(cudaMemcpy(f[k].p, hostf[k], bytes, cudaMemcpyHostToDevice));
+    }
+    double *hostt[3] = {tu, tv, tp};
+    const bool traj = tu && tv && tp && nsteps > 0;
+    if (traj)
+        for (int k = 0; k < 3; ++k)
+            if ((rc = t[k].alloc(bytes * nsteps))) return rc;
+    if (sweeps_out && nsteps > 0) NNS_CUDA(cudaMalloc(&dsw, sizeof(int32_t) * (size_t)nsteps * h->g.batch));
+    rc = nns_chorin_fd_run(h, f[0].p, f[1].p, f[2].p, f[3].p, f[4].p, nsteps, traj ? t[0].p : nullptr,
+                           traj ? t[1].p : nullptr, traj ? t[2].p : nullptr, dsw, nullptr);
+    if (rc == NNS_OK) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { set_error("kernel failed: %s", cudaGetErrorString(e)); rc = NNS_ERR_CUDA; }
+    }
+    if (rc == NNS_OK) {
+        for (int k = 0; k < 5; ++k) cudaMemcpy(hostf[k], f[k].p, bytes, cudaMemcpyDeviceToHost);
+        if (traj) for (int k = 0; k < 3; ++k) cudaMemcpy(hostt[k], t[k].p, bytes * nsteps, cudaMemcpyDeviceToHost);
+        if (dsw) cudaMemcpy(sweeps_out, dsw, sizeof(int32_t) * (size_t)nsteps * h->g.batch, cudaMemcpyDeviceToHost);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { set_error("copy back failed: %s", cudaGetErrorString(e)); rc = NNS_ERR_CUDA; }
+    }
+    cudaFree(dsw);
+    if (rc == NNS_OK && (h->params.flags & NNS_FLAG_CHECK_FINITE)) {
+        int64_t c = 0;
+        if (nns_nonfinite_count(h, &c) == NNS_OK && c > 0) {
+            set_error("non-finite values in u/v/p (%lld cells): the reference raises here (warnings are errors)", (long long)c);
+            rc = NNS_ERR_NONFINITE;
+        }
+    }
+    return rc;
+}
+
+// ---- direct_fd --------------------------------------------------------------------------------
+
+int32_t nns_direct_fd_run(nns_handle *h, double *u, double *v, double *p, int32_t nsteps, double *tu, double *tv,
+                          double *tp, void *stream) {
+    NNS_CHECK_HANDLE(h, NNS_SOLVER_DIRECT_FD);
+    if (!u || !v || !p || nsteps < 0) { set_error("nns_direct_fd_run: bad argument"); return NNS_ERR_INVALID; }
+    if ((tu || tv || tp) && !(tu && tv && tp)) { set_error("nns_direct_fd_run: pass all three trajectory buffers or none"); return NNS_ERR_INVALID; }
+    if (nsteps == 0) return NNS_OK;
+    return direct_run(h, u, v, p, nsteps, tu, tv, tp, (cudaStream_t)stream);
+}
+
+int32_t nns_direct_fd_run_host(nns_handle *h, double *u, double *v, double *p, int32_t nsteps, double *tu,
+                               double *tv, double *tp) {
+    NNS_CHECK_HANDLE(h, NNS_SOLVER_DIRECT_FD);
+    if (!u || !v || !p || nsteps < 0) { set_error("nns_direct_fd_run_host: bad argument"); return NNS_ERR_INVALID; }
+    const size_t bytes = sizeof(double) * (size_t)h->g.nx * h->g.ny * h->g.batch;
+    DevBuf f[3], t[3];
+    int rc;
+    double *hostf[3] = {u, v, p};
+    for (int k = 0; k < 3; ++k) {
+        if ((rc = f[k].alloc(bytes))) return rc;
+        NNS_CUDA(cudaMemcpy(f[k].p, hostf[k], bytes, cudaMemcpyHostToDevice));
+    }
+    double *hostt[3] = {tu, tv, tp};
+    const bool traj = tu && tv && tp && nsteps > 0;
+    if (traj)
+        for (int k = 0; k < 3; ++k)
+            if ((rc = t[k].alloc(bytes * nsteps))) return rc;
+    rc = nns_direct_fd_run(h, f[0].p, f[1].p, f[2].p, nsteps, traj ? t[0].p : nullptr, traj ? t[1].p : nullptr,
+                           traj ? t[2].p : nullptr, nullptr);
+    if (rc == NNS_OK) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { set_error("kernel failed: %s", cudaGetErrorString(e)); rc = NNS_ERR_CUDA; }
+    }
+    if (rc == NNS_OK) {
+        for (int k = 0; k < 3; ++k) cudaMemcpy(hostf[k], f[k].p, bytes, cudaMemcpyDeviceToHost);
+        if (traj) for (int k = 0; k < 3; ++k) cudaMemcpy(hostt[k], t[k].p, bytes * nsteps, cudaMemcpyDeviceToHost);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { set_error("copy back failed: %s", cudaGetErrorString(e)); rc = NNS_ERR_CUDA; }
+    }
+    if (rc == NNS_OK && (h->params.flags & NNS_FLAG_CHECK_FINITE)) {
+        int64_t c = 0;
+        if (nns_nonfinite_count(h, &c) == NNS_OK && c > 0) {
+            set_error("non-finite values in u/v/p (%lld cells)", (long long)c);
+            rc = NNS_ERR_NONFINITE;
+        }
+    }
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,300 @@
+// direct_fd.cu -- direct finite-difference Navier-Stokes step (Jacobi pressure Poisson).
+//
+// Reference semantics reproduced (src/direct_fd/simulate.py of mhw32/neural-navier-stokes):
+//   _build_up_b :56-66        RHS b (axis 1 <-> dx, axis 0 <-> dy: the transpose of boundary.py)
+//   _pressure_poisson :68-88  exactly nit Jacobi sweeps, p BCs re-applied after EVERY sweep
+//   step :90-127              upwind advection, central diffusion, -grad p / rho, then u/v BCs
+//
+// Two paths:
+//   * "chip": one CTA per member, p (ping-pong) and b resident in shared memory, all nit
+//     sweeps + BCs + velocity update fused in one launch per run of nsteps (small grids,
+//     ensembles).
+//   * "stream": fields in HBM, one launch per sweep (any grid size).
+#include "nns_common.cuh"
+
+namespace nns {
+
+struct DirectArgs {
+    Geometry g;
+    BcList ubc, vbc, pbc;
+    const double *nu_b;
+    const double *bcval;
+    int n_bcs;
+    int nsteps, nsteps_total, step0;
+    int flags;
+    double *u, *v, *p;          // [batch][nx][ny], advanced in place
+    double *su, *sv;            // scratch (ping-pong partner of u, v)
+    double *traj_u, *traj_v, *traj_p;
+    unsigned long long *nonfinite;
+};
+
+__device__ __forceinline__ void cta_apply_bc_smem(double *A, int nx, int ny, int pitch, const BcList &L,
+                                                  const double *bcval, double dx, double dy) {
+    for (int k = 0; k < L.n; ++k) {
+        const double g = bcval ? bcval[L.slot[k]] : L.value[k];
+        const int side = L.side[k];
+        const bool neu = L.type[k] == NNS_BC_NEUMANN;
+        if (side == NNS_SIDE_LEFT || side == NNS_SIDE_RIGHT) {
+            const int i = side == NNS_SIDE_LEFT ? 0 : nx - 1, in = side == NNS_SIDE_LEFT ? 1 : nx - 2;
+            const double sg = side == NNS_SIDE_LEFT ? -dx : dx;
+            for (int j = threadIdx.x; j < ny; j += blockDim.x)
+                A[i * pitch + j] = neu ? A[in * pitch + j] + sg * g : g;
+        } else {
+            const int j = side == NNS_SIDE_BOTTOM ? 0 : ny - 1, jn = side == NNS_SIDE_BOTTOM ? 1 : ny - 2;
+            const double sg = side == NNS_SIDE_BOTTOM ? -dy : dy;
+            for (int i = threadIdx.x; i < nx; i += blockDim.x)
+                A[i * pitch + j] = neu ? A[i * pitch + jn] + sg * g : g;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- chip path -------------------------------------------------------------------------
+// smem: P0, P1 (ping-pong), Bs: 3 * nx * pitch doubles.
+__global__ void __launch_bounds__(1024, 1) direct_chip_kernel(const DirectArgs a) {
+    extern __shared__ double smem[];
+    const int nx = a.g.nx, ny = a.g.ny, pitch = ny | 1;
+    const size_t N = (size_t)nx * ny;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    double *P0 = smem, *P1 = smem + nx * pitch, *Bs = smem + 2 * nx * pitch;
+    const double dt = a.g.dt, dx = a.g.dx, dy = a.g.dy, rho = a.g.rho;
+    const double nu = a.nu_b ? a.nu_b[b] : a.g.nu;
+    const double *bcval = a.bcval ? a.bcval + (size_t)b * a.n_bcs : nullptr;
+    const double dx2 = dx * dx, dy2 = dy * dy;
+    const double rden = 1.0 / (2.0 * (dx2 + dy2));
+    const double cx = dy2 * rden, cy = dx2 * rden, kb = dx2 * dy2 * rden;
+    const double r2dx = 1.0 / (2.0 * dx), r2dy = 1.0 / (2.0 * dy), rdt = 1.0 / dt;
+    double *ug = a.u + (size_t)b * N, *vg = a.v + (size_t)b * N, *pg = a.p + (size_t)b * N;
+    double *us = a.su + (size_t)b * N, *vs = a.sv + (size_t)b * N;
+
+    for (int i = warp; i < nx; i += nwarps)
+        for (int j = lane; j < ny; j += 32) P0[i * pitch + j] = pg[(size_t)i * ny + j];
+    __syncthreads();
+
+    for (int n = 0; n < a.nsteps; ++n) {
+        const double *uo = (n & 1) ? us : ug, *vo = (n & 1) ? vs : vg;   // u^n, v^n
+        double *un = (n & 1) ? ug : us, *vn = (n & 1) ? vg : vs;         // u^{n+1}
+        // RHS b (direct_fd:56-66)
+        for (int i = warp; i < nx; i += nwarps)
+            for (int j = lane; j < ny; j += 32) {
+                double bb = 0.0;
+                if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1) {
+                    const size_t q = (size_t)i * ny + j;
+                    const double ux = (uo[q + 1] - uo[q - 1]) * r2dx, vy = (vo[q + ny] - vo[q - ny]) * r2dy;
+                    const double uy = (uo[q + ny] - uo[q - ny]) * r2dy, vx = (vo[q + 1] - vo[q - 1]) * r2dx;
+                    bb = rho * (rdt * (ux + vy)) - ux * ux - 2.0 * (uy * vx) - vy * vy;
+                }
+                Bs[i * pitch + j] = kb * bb;
+            }
+        __syncthreads();
+        // exactly nit Jacobi sweeps, BCs after every sweep (direct_fd:76-86)
+        double *Pc = P0, *Pn = P1;
+        for (int s = 0; s < a.g.nit; ++s) {
+            for (int i = warp; i < nx; i += nwarps)
+                for (int j = lane; j < ny; j += 32) {
+                    const int q = i * pitch + j;
+                    double r = Pc[q];
+                    if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1)
+                        r = (Pc[q + 1] + Pc[q - 1]) * cx + (Pc[q + pitch] + Pc[q - pitch]) * cy - Bs[q];
+                    Pn[q] = r;
+                }
+            __syncthreads();
+            cta_apply_bc_smem(Pn, nx, ny, pitch, a.pbc, bcval, dx, dy);
+            double *t = Pc; Pc = Pn; Pn = t;
+        }
+        // velocity update (direct_fd:98-118) into the partner buffers, then u/v BCs (:121-125)
+        const double kpx = dt / (2.0 * rho * dx), kpy = dt / (2.0 * rho * dy);
+        const double kdx = dt / dx2, kdy = dt / dy2, ax = dt / dx, ay = dt / dy;
+        for (int i = warp; i < nx; i += nwarps)
+            for (int j = lane; j < ny; j += 32) {
+                const size_t q = (size_t)i * ny + j;
+                const double uc = uo[q], vc = vo[q];
+                double ru = uc, rv = vc;
+                if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1) {
+                    const int s = i * pitch + j;
+                    const double uW = uo[q - 1], uE = uo[q + 1], uN = uo[q - ny], uS = uo[q + ny];
+                    const double vW = vo[q - 1], vE = vo[q + 1], vN = vo[q - ny], vS = vo[q + ny];
+                    ru = uc - uc * ax * (uc - uW) - vc * ay * (uc - uN) - kpx * (Pc[s + 1] - Pc[s - 1]) +
+                         nu * (kdx * (uE - 2.0 * uc + uW) + kdy * (uS - 2.0 * uc + uN));
+                    rv = vc - uc * ax * (vc - vW) - vc * ay * (vc - vN) - kpy * (Pc[s + pitch] - Pc[s - pitch]) +
+                         nu * (kdx * (vE - 2.0 * vc + vW) + kdy * (vS - 2.0 * vc + vN));
+                }
+                un[q] = ru;
+                vn[q] = rv;
+            }
+        __syncthreads();
+        cta_apply_bc_global(un, nx, ny, a.ubc, bcval, dx, dy);
+        cta_apply_bc_global(vn, nx, ny, a.vbc, bcval, dx, dy);
+        if (a.traj_u || (a.flags & NNS_FLAG_CHECK_FINITE)) {
+            const size_t toff = ((size_t)b * a.nsteps_total + (a.step0 + n)) * N;
+            unsigned long long bad = 0;
+            for (int i = warp; i < nx; i += nwarps)
+                for (int j = lane; j < ny; j += 32) {
+                    const size_t q = (size_t)i * ny + j;
+                    const double x = un[q], y = vn[q], z = Pc[i * pitch + j];
+                    if (a.traj_u) { a.traj_u[toff + q] = x; a.traj_v[toff + q] = y; a.traj_p[toff + q] = z; }
+                    bad += !(isfinite(x) && isfinite(y) && isfinite(z));
+                }
+            if ((a.flags & NNS_FLAG_CHECK_FINITE) && bad) atomicAdd(a.nonfinite, bad);
+        }
+        if (Pc != P0) {     // keep the current pressure in P0 for the next step
+            for (int q = tid; q < nx * pitch; q += blockDim.x) P0[q] = Pc[q];
+        }
+        __syncthreads();
+    }
+    for (int i = warp; i < nx; i += nwarps)
+        for (int j = lane; j < ny; j += 32) pg[(size_t)i * ny + j] = P0[i * pitch + j];
+    if (a.nsteps & 1)
+        for (size_t q = tid; q < N; q += blockDim.x) { ug[q] = us[q]; vg[q] = vs[q]; }
+}
+
+// ---- stream path ------------------------------------------------------------------------
+__global__ void direct_rhs_kernel(const double *__restrict__ u, const double *__restrict__ v,
+                                  double *__restrict__ bout, Geometry g) {
+    const int nx = g.nx, ny = g.ny;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= ny) return;
+    const size_t base = (size_t)blockIdx.z * nx * ny, q = base + (size_t)i * ny + j;
+    const double dx2 = g.dx * g.dx, dy2 = g.dy * g.dy;
+    const double kb = dx2 * dy2 / (2.0 * (dx2 + dy2));
+    double bb = 0.0;
+    if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1) {
+        const double r2dx = 1.0 / (2.0 * g.dx), r2dy = 1.0 / (2.0 * g.dy);
+        const double ux = (u[q + 1] - u[q - 1]) * r2dx, vy = (v[q + ny] - v[q - ny]) * r2dy;
+        const double uy = (u[q + ny] - u[q - ny]) * r2dy, vx = (v[q + 1] - v[q - 1]) * r2dx;
+        bb = g.rho * ((1.0 / g.dt) * (ux + vy)) - ux * ux - 2.0 * (uy * vx) - vy * vy;
+    }
+    bout[q] = kb * bb;
+}
+
+__global__ void direct_jacobi_kernel(const double *__restrict__ pc, const double *__restrict__ bs,
+                                     double *__restrict__ pn, Geometry g) {
+    const int nx = g.nx, ny = g.ny;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= ny) return;
+    const size_t q = (size_t)blockIdx.z * nx * ny + (size_t)i * ny + j;
+    const double dx2 = g.dx * g.dx, dy2 = g.dy * g.dy;
+    const double rden = 1.0 / (2.0 * (dx2 + dy2));
+    double r = pc[q];
+    if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1)
+        r = (pc[q + 1] + pc[q - 1]) * (dy2 * rden) + (pc[q + ny] + pc[q - ny]) * (dx2 * rden) - bs[q];
+    pn[q] = r;
+}
+
+__global__ void direct_update_kernel(const double *__restrict__ uo, const double *__restrict__ vo,
+                                     const double *__restrict__ p, double *__restrict__ un,
+                                     double *__restrict__ vn, Geometry g, const double *__restrict__ nu_b) {
+    const int nx = g.nx, ny = g.ny;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= ny) return;
+    const size_t q = (size_t)blockIdx.z * nx * ny + (size_t)i * ny + j;
+    const double nu = nu_b ? nu_b[blockIdx.z] : g.nu;
+    const double dt = g.dt, dx = g.dx, dy = g.dy, rho = g.rho;
+    const double uc = uo[q], vc = vo[q];
+    double ru = uc, rv = vc;
+    if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1) {
+        const double kpx = dt / (2.0 * rho * dx), kpy = dt / (2.0 * rho * dy);
+        const double kdx = dt / (dx * dx), kdy = dt / (dy * dy), ax = dt / dx, ay = dt / dy;
+        const double uW = uo[q - 1], uE = uo[q + 1], uN = uo[q - ny], uS = uo[q + ny];
+        const double vW = vo[q - 1], vE = vo[q + 1], vN = vo[q - ny], vS = vo[q + ny];
+        ru = uc - uc * ax * (uc - uW) - vc * ay * (uc - uN) - kpx * (p[q + 1] - p[q - 1]) +
+             nu * (kdx * (uE - 2.0 * uc + uW) + kdy * (uS - 2.0 * uc + uN));
+        rv = vc - uc * ax * (vc - vW) - vc * ay * (vc - vN) - kpy * (p[q + ny] - p[q - ny]) +
+             nu * (kdx * (vE - 2.0 * vc + vW) + kdy * (vS - 2.0 * vc + vN));
+    }
+    un[q] = ru;
+    vn[q] = rv;
+}
+
+__global__ void apply_bc_kernel(double *A, Geometry g, BcList L, const double *bcval, int n_bcs) {
+    const size_t N = (size_t)g.nx * g.ny;
+    cta_apply_bc_global(A + blockIdx.x * N, g.nx, g.ny, L, bcval ? bcval + (size_t)blockIdx.x * n_bcs : nullptr,
+                        g.dx, g.dy);
+}
+
+__global__ void snapshot_kernel(const double *__restrict__ u, const double *__restrict__ v,
+                                const double *__restrict__ p, double *tu, double *tv, double *tp, size_t N,
+                                int nsteps_total, int step, unsigned long long *nonfinite, int flags) {
+    const size_t b = blockIdx.y;
+    const size_t toff = (b * nsteps_total + step) * N;
+    unsigned long long bad = 0;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += (size_t)gridDim.x * blockDim.x) {
+        const double x = u[b * N + q], y = v[b * N + q], z = p[b * N + q];
+        if (tu) { tu[toff + q] = x; tv[toff + q] = y; tp[toff + q] = z; }
+        bad += !(isfinite(x) && isfinite(y) && isfinite(z));
+    }
+    if ((flags & NNS_FLAG_CHECK_FINITE) && bad) atomicAdd(nonfinite, bad);
+}
+
+int launch_apply_bc(nns_handle *h, int field, double *a, cudaStream_t st) {
+    if (h->bc[field].n == 0) return NNS_OK;
+    apply_bc_kernel<<<h->g.batch, 128, 0, st>>>(a, h->g, h->bc[field], h->d_bcval, h->n_bcs);
+    NNS_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return NNS_OK;
+}
+
+static int ensure(double **p, size_t bytes) {
+    if (*p) return NNS_OK;
+    NNS_CUDA(cudaMalloc(p, bytes));
+    return NNS_OK;
+}
+
+int direct_run(nns_handle *h, double *u, double *v, double *p, int nsteps, double *tu, double *tv, double *tp,
+               cudaStream_t st) {
+    const Geometry &g = h->g;
+    const size_t N = (size_t)g.nx * g.ny, bytes = sizeof(double) * N * g.batch;
+    int rc;
+    if ((rc = ensure(&h->d_scratch[0], bytes)) || (rc = ensure(&h->d_scratch[1], bytes))) return rc;
+    const int pitch = g.ny | 1;
+    const size_t smem = sizeof(double) * 3 * (size_t)g.nx * pitch;
+    if (smem <= (size_t)h->max_smem_optin) {
+        DirectArgs a{};
+        a.g = g; a.ubc = h->bc[0]; a.vbc = h->bc[1]; a.pbc = h->bc[2];
+        a.nu_b = h->d_nu; a.bcval = h->d_bcval; a.n_bcs = h->n_bcs;
+        a.nsteps = nsteps; a.nsteps_total = nsteps; a.step0 = 0; a.flags = h->params.flags;
+        a.u = u; a.v = v; a.p = p; a.su = h->d_scratch[0]; a.sv = h->d_scratch[1];
+        a.traj_u = tu; a.traj_v = tv; a.traj_p = tp; a.nonfinite = h->d_nonfinite;
+        const long cells = (long)g.nx * g.ny;
+        const int threads = cells >= 8192 ? 1024 : cells >= 1024 ? 512 : 256;
+        NNS_CUDA(cudaFuncSetAttribute(direct_chip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        direct_chip_kernel<<<g.batch, threads, smem, st>>>(a);
+        NNS_CUDA(cudaGetLastError());
+        h->launches += 1;
+        return NNS_OK;
+    }
+    // stream path
+    if ((rc = ensure(&h->d_b, bytes)) || (rc = ensure(&h->d_p2, bytes))) return rc;
+    const dim3 blk(128), grd((g.ny + 127) / 128, g.nx, g.batch);
+    double *uc = u, *vc = v, *un = h->d_scratch[0], *vn = h->d_scratch[1];
+    for (int n = 0; n < nsteps; ++n) {
+        direct_rhs_kernel<<<grd, blk, 0, st>>>(uc, vc, h->d_b, g);
+        double *pc = p, *pn = h->d_p2;
+        for (int s = 0; s < g.nit; ++s) {
+            direct_jacobi_kernel<<<grd, blk, 0, st>>>(pc, h->d_b, pn, g);
+            h->launches += 1;
+            if ((rc = launch_apply_bc(h, 2, pn, st))) return rc;
+            double *t = pc; pc = pn; pn = t;
+        }
+        if (pc != p) NNS_CUDA(cudaMemcpyAsync(p, pc, bytes, cudaMemcpyDeviceToDevice, st));
+        direct_update_kernel<<<grd, blk, 0, st>>>(uc, vc, p, un, vn, g, h->d_nu);
+        h->launches += 2;
+        if ((rc = launch_apply_bc(h, 0, un, st)) || (rc = launch_apply_bc(h, 1, vn, st))) return rc;
+        if (tu || (h->params.flags & NNS_FLAG_CHECK_FINITE)) {
+            snapshot_kernel<<<dim3(64, g.batch), 256, 0, st>>>(un, vn, p, tu, tv, tp, N, nsteps, n,
+                                                               h->d_nonfinite, h->params.flags);
+            h->launches += 1;
+        }
+        double *t;
+        t = uc; uc = un; un = t;
+        t = vc; vc = vn; vn = t;
+    }
+    NNS_CUDA(cudaGetLastError());
+    if (uc != u) {
+        NNS_CUDA(cudaMemcpyAsync(u, uc, bytes, cudaMemcpyDeviceToDevice, st));
+        NNS_CUDA(cudaMemcpyAsync(v, vc, bytes, cudaMemcpyDeviceToDevice, st));
+    }
+    return NNS_OK;
+}
+
+}  // namespace nns
