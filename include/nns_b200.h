@@ -106,6 +106,13 @@ int32_t nns_chorin_fd_step(nns_handle *h, const double *u, const double *v, cons
                            const double *v1, double *p, double *u_out, double *v_out, int32_t *sweeps_out,
                            void *stream);
 
+/* The same step with HOST buffers (synchronous): the call the reference's step() would make.
+ * 5 fields in (u, v, u1, v1, p), 3 out (u_out, v_out, p in place); sweeps_out host int32 [batch]
+ * or NULL.  Member chunks are pipelined over internal streams; use pinned memory for speed. */
+int32_t nns_chorin_fd_step_host(nns_handle *h, const double *u, const double *v, const double *u1,
+                                const double *v1, double *p, double *u_out, double *v_out,
+                                int32_t *sweeps_out);
+
 /* nsteps time steps, replaces the loop of NavierStokesSystem.simulate (:258-265).  On
  * return u,v hold step n, u1,v1 step n-1, p step n.  traj_*: device [batch][nsteps][nx][ny]
  * or NULL (the reference keeps every step, :263-265).  sweeps_out: device int32

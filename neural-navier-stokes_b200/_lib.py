@@ -42,6 +42,7 @@ _PROTOS = {
     "nns_nonfinite_count": (_i32, [_vp, C.POINTER(_i64)]),
     "nns_apply_bc": (_i32, [_vp, _i32, _vp, _vp]),
     "nns_chorin_fd_step": (_i32, [_vp] * 10),
+    "nns_chorin_fd_step_host": (_i32, [_vp] * 9),
     "nns_chorin_fd_run": (_i32, [_vp] * 6 + [_i32] + [_vp] * 5),
     "nns_chorin_fd_run_host": (_i32, [_vp] * 6 + [_i32] + [_vp] * 4),
     "nns_chorin_fd_predictor": (_i32, [_vp] * 8),

@@ -22,12 +22,12 @@ void set_error(const char *fmt, ...) {
 struct ChipArgs;
 int chorin_chip_run(nns_handle *h, double *bufU[3], double *bufV[3], double *p, int nsteps, int nsteps_total,
                     int step0, int phases, int fixup, double *tu, double *tv, double *tp, int32_t *sweeps,
-                    cudaStream_t st);
+                    cudaStream_t st, int m0, int count);
 bool chorin_chip_fits(const nns_handle *h);
 // chorin_fd_tiled.cu
 int chorin_tiled_run(nns_handle *h, double *bufU[3], double *bufV[3], double *p, int nsteps, int nsteps_total,
                      int step0, int phases, int fixup, double *tu, double *tv, double *tp, int32_t *sweeps,
-                     cudaStream_t st);
+                     cudaStream_t st, int m0, int count);
 // direct_fd.cu
 int direct_run(nns_handle *h, double *u, double *v, double *p, int nsteps, double *tu, double *tv, double *tp,
                cudaStream_t st);
@@ -41,10 +41,12 @@ static int ensure_scratch(nns_handle *h, int k) {
 
 static int chorin_dispatch(nns_handle *h, double *bufU[3], double *bufV[3], double *p, int nsteps,
                            int nsteps_total, int step0, int phases, int fixup, double *tu, double *tv,
-                           double *tp, int32_t *sweeps, cudaStream_t st) {
+                           double *tp, int32_t *sweeps, cudaStream_t st, int m0 = 0, int count = -1) {
     if (chorin_chip_fits(h))
-        return chorin_chip_run(h, bufU, bufV, p, nsteps, nsteps_total, step0, phases, fixup, tu, tv, tp, sweeps, st);
-    return chorin_tiled_run(h, bufU, bufV, p, nsteps, nsteps_total, step0, phases, fixup, tu, tv, tp, sweeps, st);
+        return chorin_chip_run(h, bufU, bufV, p, nsteps, nsteps_total, step0, phases, fixup, tu, tv, tp, sweeps, st,
+                               m0, count);
+    return chorin_tiled_run(h, bufU, bufV, p, nsteps, nsteps_total, step0, phases, fixup, tu, tv, tp, sweeps, st,
+                            m0, count);
 }
 
 }  // namespace nns
@@ -141,6 +143,8 @@ int32_t nns_destroy(nns_handle *h) {
     cudaFree(h->d_nu); cudaFree(h->d_bcval); cudaFree(h->d_cprime); cudaFree(h->d_b); cudaFree(h->d_p2);
     cudaFree(h->d_sweeps); cudaFree(h->d_nonfinite);
     for (int k = 0; k < 4; ++k) cudaFree(h->d_scratch[k]);
+    for (int k = 0; k < 7; ++k) cudaFree(h->d_stage[k]);
+    for (int k = 0; k < 4; ++k) if (h->streams[k]) cudaStreamDestroy(h->streams[k]);
     delete h;
     return NNS_OK;
 }
@@ -265,6 +269,52 @@ int32_t nns_chorin_fd_run_host(nns_handle *h, double *u, double *v, double *u1, 
             set_error("non-finite values in u/v/p (%lld cells): the reference raises here (warnings are errors)", (long long)c);
             rc = NNS_ERR_NONFINITE;
         }
+    }
+    return rc;
+}
+
+// One step with HOST buffers, mirroring the reference's step(un, vn, un1, vn1, p) -> (u, v, p):
+// 5 fields in, 3 fields out (u_out, v_out, p in place).  The batch is cut into member chunks
+// that are pipelined over several streams (H2D of chunk c+1 || kernel of chunk c || D2H of
+// chunk c-1), so with pinned host memory the call runs at the PCIe rate.
+int32_t nns_chorin_fd_step_host(nns_handle *h, const double *u, const double *v, const double *u1,
+                                const double *v1, double *p, double *u_out, double *v_out, int32_t *sweeps_out) {
+    NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_FD);
+    if (!u || !v || !u1 || !v1 || !p || !u_out || !v_out) { set_error("nns_chorin_fd_step_host: null field"); return NNS_ERR_INVALID; }
+    const size_t N = (size_t)h->g.nx * h->g.ny, B = h->g.batch;
+    const size_t bytes = sizeof(double) * N * B;
+    for (int k = 0; k < 7; ++k)
+        if (!h->d_stage[k]) NNS_CUDA(cudaMalloc(&h->d_stage[k], bytes));
+    for (int k = 0; k < 4; ++k)
+        if (!h->streams[k]) NNS_CUDA(cudaStreamCreateWithFlags(&h->streams[k], cudaStreamNonBlocking));
+    double **d = h->d_stage;       // u, v, u1, v1, p, u_out, v_out
+    const double *hin[5] = {u, v, u1, v1, p};
+    double *hout[3] = {u_out, v_out, p};
+    const int dout[3] = {5, 6, 4};
+    const int nchunks = B >= 1184 ? 8 : B >= 296 ? 2 : 1;     // keep >= 148 CTAs per launch
+    const size_t per = (B + nchunks - 1) / nchunks;
+    int rc = NNS_OK;
+    for (int c = 0; c < nchunks && rc == NNS_OK; ++c) {
+        const size_t m0 = c * per, cnt = m0 + per <= B ? per : B - m0;
+        if (m0 >= B) break;
+        cudaStream_t st = h->streams[c % 4];
+        const size_t off = m0 * N, cb = sizeof(double) * cnt * N;
+        for (int k = 0; k < 5; ++k) NNS_CUDA(cudaMemcpyAsync(d[k] + off, hin[k] + off, cb, cudaMemcpyHostToDevice, st));
+        double *bu[3] = {d[0] + off, d[2] + off, d[5] + off};
+        double *bv[3] = {d[1] + off, d[3] + off, d[6] + off};
+        rc = chorin_dispatch(h, bu, bv, d[4] + off, 1, 1, 0, 7, 0, nullptr, nullptr, nullptr,
+                             h->d_sweeps + m0, st, (int)m0, (int)cnt);
+        if (rc != NNS_OK) break;
+        for (int k = 0; k < 3; ++k) NNS_CUDA(cudaMemcpyAsync(hout[k] + off, d[dout[k]] + off, cb, cudaMemcpyDeviceToHost, st));
+        if (sweeps_out) NNS_CUDA(cudaMemcpyAsync(sweeps_out + m0, h->d_sweeps + m0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, st));
+    }
+    for (int k = 0; k < 4; ++k) {
+        cudaError_t e = cudaStreamSynchronize(h->streams[k]);
+        if (e != cudaSuccess && rc == NNS_OK) { set_error("step_host: %s", cudaGetErrorString(e)); rc = NNS_ERR_CUDA; }
+    }
+    if (rc == NNS_OK && (h->params.flags & NNS_FLAG_CHECK_FINITE)) {
+        int64_t c = 0;
+        if (nns_nonfinite_count(h, &c) == NNS_OK && c > 0) { set_error("non-finite values in u/v/p (%lld cells)", (long long)c); rc = NNS_ERR_NONFINITE; }
     }
     return rc;
 }

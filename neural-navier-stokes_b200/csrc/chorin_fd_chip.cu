@@ -371,7 +371,7 @@ ChipPlan chorin_chip_plan(const nns_handle *h) {
     return pl;
 }
 
-int chorin_chip_launch(nns_handle *h, ChipArgs &a, cudaStream_t st) {
+int chorin_chip_launch(nns_handle *h, ChipArgs &a, cudaStream_t st, int m0, int count) {
     const ChipPlan pl = chorin_chip_plan(h);
     if (!pl.fits) {
         set_error("chorin_fd chip path: grid %dx%d needs %zu B of shared memory (> %d)", h->g.nx, h->g.ny,
@@ -382,15 +382,15 @@ int chorin_chip_launch(nns_handle *h, ChipArgs &a, cudaStream_t st) {
     a.HS = pl.HS;
     if (!pl.cp_smem && !h->d_cprime)
         NNS_CUDA(cudaMalloc(&h->d_cprime, sizeof(double) * 2 * (size_t)pl.HS * h->g.batch));
-    a.cprime = h->d_cprime;
+    a.cprime = h->d_cprime ? h->d_cprime + (size_t)m0 * 2 * pl.HS : nullptr;
     if (pl.cp_smem) {
         NNS_CUDA(cudaFuncSetAttribute(chorin_chip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)pl.smem_bytes));
-        chorin_chip_kernel<true><<<h->g.batch, pl.threads, pl.smem_bytes, st>>>(a);
+        chorin_chip_kernel<true><<<count, pl.threads, pl.smem_bytes, st>>>(a);
     } else {
         NNS_CUDA(cudaFuncSetAttribute(chorin_chip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)pl.smem_bytes));
-        chorin_chip_kernel<false><<<h->g.batch, pl.threads, pl.smem_bytes, st>>>(a);
+        chorin_chip_kernel<false><<<count, pl.threads, pl.smem_bytes, st>>>(a);
     }
     NNS_CUDA(cudaGetLastError());
     h->launches += 1;
@@ -401,11 +401,16 @@ bool chorin_chip_fits(const nns_handle *h) { return chorin_chip_plan(h).fits; }
 
 int chorin_chip_run(nns_handle *h, double *bufU[3], double *bufV[3], double *p, int nsteps, int nsteps_total,
                     int step0, int phases, int fixup, double *tu, double *tv, double *tp, int32_t *sweeps,
-                    cudaStream_t st) {
+                    cudaStream_t st, int m0, int count) {
+    // Members [m0, m0+count): field / trajectory / sweeps pointers are already offset by the
+    // caller; the per-member parameter tables are offset here.
+    if (count < 0) count = h->g.batch - m0;
     ChipArgs a{};
     a.g = h->g;
     a.ubc = h->bc[0]; a.vbc = h->bc[1]; a.pbc = h->bc[2];
-    a.nu_b = h->d_nu; a.bcval = h->d_bcval; a.n_bcs = h->n_bcs;
+    a.nu_b = h->d_nu ? h->d_nu + m0 : nullptr;
+    a.bcval = h->d_bcval ? h->d_bcval + (size_t)m0 * h->n_bcs : nullptr;
+    a.n_bcs = h->n_bcs;
     a.nsteps = nsteps; a.nsteps_total = nsteps_total; a.step0 = step0;
     a.phases = phases; a.fixup = fixup; a.flags = h->params.flags;
     for (int k = 0; k < 3; ++k) { a.bufU[k] = bufU[k]; a.bufV[k] = bufV[k]; }
@@ -413,7 +418,7 @@ int chorin_chip_run(nns_handle *h, double *bufU[3], double *bufV[3], double *p, 
     a.traj_u = tu; a.traj_v = tv; a.traj_p = tp;
     a.sweeps = sweeps;
     a.nonfinite = h->d_nonfinite;
-    return chorin_chip_launch(h, a, st);
+    return chorin_chip_launch(h, a, st, m0, count);
 }
 
 }  // namespace nns

@@ -36,6 +36,8 @@ struct nns_handle {
     double *d_nu;             // [batch] or nullptr
     double *d_bcval;          // [batch][n_bcs] or nullptr
     double *d_scratch[4];     // rotation / ui,vi workspace, [batch][nx][ny] each, lazily allocated
+    double *d_stage[7];       // device staging of the host-buffer entry points
+    cudaStream_t streams[4];  // copy/compute pipelining of the host-buffer entry points
     double *d_cprime;         // SOR right-hand side when it does not fit in shared memory
     double *d_b;              // direct_fd rhs / second p buffer
     double *d_p2;
