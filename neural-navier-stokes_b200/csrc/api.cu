@@ -24,6 +24,7 @@ int chorin_chip_run(nns_handle *h, double *bufU[3], double *bufV[3], double *p, 
                     int step0, int phases, int fixup, double *tu, double *tv, double *tp, int32_t *sweeps,
                     cudaStream_t st, int m0, int count);
 bool chorin_chip_fits(const nns_handle *h);
+void chorin_chip_free_plan(nns_handle *h);
 // chorin_fd_tiled.cu
 int chorin_tiled_run(nns_handle *h, double *bufU[3], double *bufV[3], double *p, int nsteps, int nsteps_total,
                      int step0, int phases, int fixup, double *tu, double *tv, double *tp, int32_t *sweeps,
@@ -141,7 +142,8 @@ int32_t nns_destroy(nns_handle *h) {
     if (!h) return NNS_OK;
     cudaSetDevice(h->device);
     cudaFree(h->d_nu); cudaFree(h->d_bcval); cudaFree(h->d_cprime); cudaFree(h->d_b); cudaFree(h->d_p2);
-    cudaFree(h->d_sweeps); cudaFree(h->d_nonfinite);
+    cudaFree(h->d_sweeps); cudaFree(h->d_nonfinite); cudaFree(h->d_blockdesc);
+    chorin_chip_free_plan(h);
     for (int k = 0; k < 4; ++k) cudaFree(h->d_scratch[k]);
     for (int k = 0; k < 7; ++k) cudaFree(h->d_stage[k]);
     for (int k = 0; k < 4; ++k) if (h->streams[k]) cudaStreamDestroy(h->streams[k]);

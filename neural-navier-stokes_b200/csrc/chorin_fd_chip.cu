@@ -1,6 +1,6 @@
 // chorin_fd_chip.cu -- chorin_fd time step with the whole pressure grid of one member resident
-// in one SM's shared memory ("chip" path): one CTA per ensemble member, all phases of the
-// step fused in one launch, nsteps steps per launch.
+// on ONE SM ("chip" path): one CTA per ensemble member, all phases of the step fused in one
+// launch, nsteps steps per launch.
 //
 // Reference semantics reproduced (src/chorin_fd/simulate.py of mhw32/neural-navier-stokes):
 //   phase A  _explicit_predictor_step :63-91 (x-only advection differences kept) or
@@ -10,17 +10,34 @@
 //            (cell (i,j) of sweep s): every dependency of the lexicographic order lies at
 //            t-1 or t-2, so all sweeps are pipelined through ONE pass over the grid with a
 //            single __syncthreads per stage and the result equals the sequential order.
+//            In steady state a stage updates every cell of one (i+j) parity -- a red-black
+//            pattern whose per-cell sweep index is (t-i-j)/2.
 //   phase C  p_bc in list order :230-231, _correction_step :204-210, trajectory snapshot
 //            :263-265.
 //
-// Shared-memory layout of p ("split rows"): two half arrays by column parity,
-//   P[h][i][jh],  h = j & 1, jh = j >> 1, pitch PH, half stride HS.
-// At stage t the active cells of row i are j = (t-i) - 2s, s = s_lo..s_hi: one parity, i.e. a
-// CONTIGUOUS run of jh in one half array, so a warp's 32 lanes (= 32 consecutive sweeps)
-// read and write consecutive 8-byte words: conflict-free LDS/STS without padding.
+// Two implementations of phase B:
+//   REG  (register blocks): each thread owns a BR x BC block of p in REGISTERS for the whole
+//        solve; only block-perimeter cells go through shared memory (halo slots, one barrier
+//        per stage), the right-hand side C' sits in shared memory in a thread-private,
+//        conflict-free 16-byte layout.  Threads are ordered by block anti-diagonal so that a
+//        warp's 32 blocks enter and leave the active band together.
+//   SPLIT (generic fallback, any nx/ny that fits): p in shared memory as two half arrays by
+//        column parity (P[h][i][j>>1]); the active cells of a row at a stage are a contiguous
+//        run in one half array, a warp's lanes are consecutive sweeps.
+#include <stdlib.h>
+
+#include <algorithm>
+#include <vector>
+
 #include "nns_common.cuh"
 
 namespace nns {
+
+struct BlockDesc {      // REG path: one per thread, built on the host (chorin_chip_plan)
+    short r0, c0;       // first row / column of the block (interior starts at 1)
+    short nN, nS, nW, nE;   // thread ids of the neighbouring blocks, -1 = physical boundary / none
+    short bd;           // block anti-diagonal bi + bj
+};
 
 struct ChipArgs {
     Geometry g;
@@ -28,47 +45,56 @@ struct ChipArgs {
     const double *nu_b;      // [batch] or null
     const double *bcval;     // [batch][n_bcs] or null
     int n_bcs;
-    int PH, HS;              // half-row pitch, half-array stride (doubles)
+    int PH, HS;              // SPLIT: half-row pitch, half-array stride (doubles)
+    int nblocks;             // REG: number of blocks (threads that own cells)
+    const BlockDesc *desc;   // REG
     int nsteps, nsteps_total, step0;
     int phases;              // bit0 A, bit1 B, bit2 C
     int fixup;               // copy final cur/prev into buffers 0/1
     int flags;
     double *bufU[3], *bufV[3];   // roles at entry: 0 = cur (u^n), 1 = prev (u^{n-1}), 2 = next
     double *p;
-    double *cprime;          // global C' scratch [batch][2*HS] when it does not fit in smem
+    double *cprime;          // SPLIT: global C' scratch [batch][2*HS] when it does not fit in smem
     double *traj_u, *traj_v, *traj_p;   // [batch][nsteps_total][nx][ny] or null
     int32_t *sweeps;         // [nsteps_total][batch] or null
     unsigned long long *nonfinite;
+};
+
+struct Coef {
+    double ca, cb, cc, cu, cv, beta, tol;
 };
 
 __device__ __forceinline__ int split_off(int i, int j, int PH, int HS) {
     return (j & 1) * HS + i * PH + (j >> 1);
 }
 
-// Thomas solve along axis 0 for all interior columns, constant tridiagonal (-off, diag, -off)
-// i.e. np.linalg.solve(A, rhs) of chorin_fd/simulate.py:137,153,159,165 (A diagonally
+// "this update still violates the exit test": !(|d| <= tol), so NaN counts as a violation.  One
+// DSETP whose result is OR-accumulated into a predicate; no branch (a branchy version of this
+// test made the tracked sweeps 4x slower through divergence).
+__device__ __forceinline__ bool exceeds(double d, double tol) { return !(fabs(d) <= tol); }
+
+// Thomas solve along axis 0 for all interior columns, constant tridiagonal (off, diag, off),
+// i.e. np.linalg.solve(A, rhs) of chorin_fd/simulate.py:137,153,159,165 (A is diagonally
 // dominant => LAPACK's partial pivoting never swaps, so this is the same elimination).
-// rhs/x are row-major [nx][ny] interiors; cpr holds the nx forward-sweep coefficients.
 __device__ void cta_thomas_axis0(double *x, int nx, int ny, double diag, double off, double *cpr) {
-    // forward coefficients (same for every column); thread 0 builds them once per call
     if (threadIdx.x == 0) {
         double c = 0.0;
         for (int i = 1; i < nx - 1; ++i) {
-            const double m = diag - off * c;   // pivot after eliminating the sub-diagonal
+            const double m = diag - off * c;
             c = off / m;
-            cpr[i] = c;                        // c_i' = off / m_i
-            cpr[nx + i] = 1.0 / m;             // 1 / m_i
+            cpr[i] = c;
+            cpr[nx + i] = 1.0 / m;
         }
     }
     __syncthreads();
     for (int j = 1 + threadIdx.x; j < ny - 1; j += blockDim.x) {
         double d = 0.0;
-        for (int i = 1; i < nx - 1; ++i) {     // forward: d_i' = (d_i - off*d_{i-1}') / m_i
+        for (int i = 1; i < nx - 1; ++i) {
             d = (x[(size_t)i * ny + j] - off * d) * cpr[nx + i];
             x[(size_t)i * ny + j] = d;
         }
         double xn = 0.0;
-        for (int i = nx - 2; i >= 1; --i) {    // backward: x_i = d_i' - c_i' x_{i+1}
+        for (int i = nx - 2; i >= 1; --i) {
             xn = x[(size_t)i * ny + j] - cpr[i] * xn;
             x[(size_t)i * ny + j] = xn;
         }
@@ -76,10 +102,146 @@ __device__ void cta_thomas_axis0(double *x, int nx, int ny, double diag, double 
     __syncthreads();
 }
 
+// ---- phase A ------------------------------------------------------------------------------
+__device__ void phase_predictor(const ChipArgs &a, const double *uc, const double *vc, const double *up,
+                                const double *vp, double *un, double *vn, double nu, const double *bcval,
+                                double *aux) {
+    const int nx = a.g.nx, ny = a.g.ny;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const double dt = a.g.dt, dx = a.g.dx, dy = a.g.dy;
+    const double dx2 = dx * dx, dy2 = dy * dy;
+    const double r2dx = 1.0 / (2.0 * dx), r2dy = 1.0 / (2.0 * dy), rdx2 = 1.0 / dx2, rdy2 = 1.0 / dy2;
+    if (a.g.method == NNS_METHOD_EXPLICIT) {
+        for (int i = warp; i < nx; i += nwarps)
+            for (int j = lane; j < ny; j += 32) {
+                const size_t q = (size_t)i * ny + j;
+                const double u0 = uc[q], v0 = vc[q];
+                double ru = u0, rv = v0;
+                if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1) {
+                    const double u1c = up[q], v1c = vp[q];
+                    const double uS = uc[q + ny], uN = uc[q - ny], uE = uc[q + 1], uW = uc[q - 1];
+                    const double vS = vc[q + ny], vN = vc[q - ny], vE = vc[q + 1], vW = vc[q - 1];
+                    const double pS = up[q + ny], pN = up[q - ny], pE = up[q + 1], pW = up[q - 1];
+                    const double qS = vp[q + ny], qN = vp[q - ny], qE = vp[q + 1], qW = vp[q - 1];
+                    // both advection terms difference along axis 0 (chorin_fd:74,76,83,85)
+                    const double k0 = u0 * r2dx + v0 * r2dy, k1 = u1c * r2dx + v1c * r2dy;
+                    const double advu = 1.5 * (k0 * (uS - uN)) - 0.5 * (k1 * (pS - pN));
+                    const double advv = 1.5 * (k0 * (vS - vN)) - 0.5 * (k1 * (qS - qN));
+                    const double lapu = 1.5 * ((uS - 2.0 * u0 + uN) * rdx2 + (uE - 2.0 * u0 + uW) * rdy2) -
+                                        0.5 * ((pS - 2.0 * u1c + pN) * rdx2 + (pE - 2.0 * u1c + pW) * rdy2);
+                    const double lapv = 1.5 * ((vS - 2.0 * v0 + vN) * rdx2 + (vE - 2.0 * v0 + vW) * rdy2) -
+                                        0.5 * ((qS - 2.0 * v1c + qN) * rdx2 + (qE - 2.0 * v1c + qW) * rdy2);
+                    ru = u0 - dt * advu + (dt * nu) * lapu;
+                    rv = v0 - dt * advv + (dt * nu) * lapv;
+                }
+                un[q] = ru;
+                vn[q] = rv;
+            }
+        __syncthreads();
+    } else {
+        // semi-implicit: AB2 advection + Crank-Nicolson ADI, all four solves along axis 0
+        // (chorin_fd:93-167; diagonal (2/nu)dx^2+2dt :108, vC scaled by dx^2 :150).
+        const double kx = 2.0 / nu * dx2, ky = 2.0 / nu * dy2;
+        for (int i = warp; i < nx; i += nwarps)
+            for (int j = lane; j < ny; j += 32) {
+                const size_t q = (size_t)i * ny + j;
+                const double u0 = uc[q], v0 = vc[q];
+                double ru = u0, rv = v0;
+                if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1) {
+                    const double u1c = up[q], v1c = vp[q];
+                    const double uS = uc[q + ny], uN = uc[q - ny], uE = uc[q + 1], uW = uc[q - 1];
+                    const double vS = vc[q + ny], vN = vc[q - ny], vE = vc[q + 1], vW = vc[q - 1];
+                    const double pS = up[q + ny], pN = up[q - ny], pE = up[q + 1], pW = up[q - 1];
+                    const double qS = vp[q + ny], qN = vp[q - ny], qE = vp[q + 1], qW = vp[q - 1];
+                    const double uHn = u0 * (uS - uN) * r2dx + v0 * (uE - uW) * r2dy;
+                    const double uHn1 = u1c * (pS - pN) * r2dx + v1c * (pE - pW) * r2dy;
+                    const double vHn = u0 * (vS - vN) * r2dx + v0 * (vE - vW) * r2dy;
+                    const double vHn1 = u1c * (qS - qN) * r2dx + v1c * (qE - qW) * r2dy;
+                    const double uC2 = dt * nu * ((uS - 2.0 * u0 + uN) * rdx2 + (uE - 2.0 * u0 + uW) * rdy2);
+                    const double vC2 = dt * nu * ((vS - 2.0 * v0 + vN) * rdx2 + (vE - 2.0 * v0 + vW) * rdy2);
+                    ru = kx * (0.5 * dt * (3.0 * uHn - uHn1) + uC2);
+                    rv = kx * (0.5 * dt * (3.0 * vHn - vHn1) + vC2);
+                }
+                un[q] = ru;
+                vn[q] = rv;
+            }
+        __syncthreads();
+        cta_thomas_axis0(un, nx, ny, kx + 2.0 * dt, -dt, aux);   // ut
+        cta_thomas_axis0(vn, nx, ny, kx + 2.0 * dt, -dt, aux);   // vt
+        for (int i = 1 + warp; i < nx - 1; i += nwarps)
+            for (int j = 1 + lane; j < ny - 1; j += 32) {
+                const size_t q = (size_t)i * ny + j;
+                const double u0 = uc[q], v0 = vc[q];
+                un[q] = ky * (un[q] + u0) - dt * (uc[q + 1] - 2.0 * u0 + uc[q - 1]);
+                vn[q] = ky * (vn[q] + v0) - dt * (vc[q + 1] - 2.0 * v0 + vc[q - 1]);
+            }
+        __syncthreads();
+        cta_thomas_axis0(un, nx, ny, ky + 2.0 * dt, -dt, aux);   // B is applied along axis 0 (:159)
+        cta_thomas_axis0(vn, nx, ny, ky + 2.0 * dt, -dt, aux);
+    }
+    cta_apply_bc_global(un, nx, ny, a.ubc, bcval, dx, dy);
+    cta_apply_bc_global(vn, nx, ny, a.vbc, bcval, dx, dy);
+}
+
+// ---- phase C (p already in global memory, no BCs yet) -----------------------------------------
+__device__ void phase_finish(const ChipArgs &a, double *pg, double *un, double *vn, const double *bcval,
+                             size_t toff) {
+    const int nx = a.g.nx, ny = a.g.ny;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const double dt = a.g.dt, dx = a.g.dx, dy = a.g.dy;
+    const bool correct = a.phases & 4;
+    if (correct) cta_apply_bc_global(pg, nx, ny, a.pbc, bcval, dx, dy);
+    if (!correct && !a.traj_p) return;
+    const double kx = dt / (2.0 * dx), ky = dt / (2.0 * dy);
+    unsigned long long bad = 0;
+    for (int i = warp; i < nx; i += nwarps)
+        for (int j = lane; j < ny; j += 32) {
+            const size_t q = (size_t)i * ny + j;
+            const double pc = pg[q];
+            if (a.traj_p) a.traj_p[toff + q] = pc;
+            if (correct) {
+                double ru = un[q], rv = vn[q];
+                if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1) {
+                    ru -= kx * (pg[q + ny] - pg[q - ny]);
+                    rv -= ky * (pg[q + 1] - pg[q - 1]);
+                    un[q] = ru;
+                    vn[q] = rv;
+                }
+                if (a.traj_u) a.traj_u[toff + q] = ru;
+                if (a.traj_v) a.traj_v[toff + q] = rv;
+                if (a.flags & NNS_FLAG_CHECK_FINITE) bad += !(isfinite(ru) && isfinite(rv) && isfinite(pc));
+            }
+        }
+    if ((a.flags & NNS_FLAG_CHECK_FINITE) && bad) atomicAdd(a.nonfinite, bad);
+}
+
+// Turn the per-thread violation bits into the number of sweeps the reference loop would run.
+__device__ int sweeps_needed(unsigned long long mask, int cap, const int *viol, unsigned long long *s_mask,
+                             int *s_need) {
+    unsigned lo = (unsigned)mask, hi = (unsigned)(mask >> 32);
+    lo = __reduce_or_sync(0xffffffffu, lo);
+    hi = __reduce_or_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) atomicOr(s_mask, ((unsigned long long)hi << 32) | lo);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int nd = cap;
+        const int c64 = cap < 64 ? cap : 64;
+        const unsigned long long full = c64 == 64 ? ~0ull : ((1ull << c64) - 1ull);
+        const unsigned long long clr = ~(*s_mask) & full;
+        if (clr) nd = __ffsll((long long)clr);      // first sweep s with max|dp| <= tol: s+1 sweeps run
+        else
+            for (int s = 64; s < cap; ++s)
+                if (!viol[s - 64]) { nd = s + 1; break; }
+        *s_need = nd;
+    }
+    __syncthreads();
+    return *s_need;
+}
+
+// ============================ SPLIT implementation of phase B ==================================
 template <bool TRACK>
-__device__ __forceinline__ void sor_wavefront(double *Ps, const double *Cs, int nx, int ny, int PH, int HS,
-                                              int cap, double ca, double cb, double beta, double tol,
-                                              unsigned long long &mask, int *viol) {
+__device__ __forceinline__ void sor_wavefront_split(double *Ps, const double *Cs, int nx, int ny, int PH, int HS,
+                                                    int cap, const Coef &k, unsigned long long &mask, int *viol) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int tmax = (nx - 2) + (ny - 2) + 2 * (cap - 1);
     const int span = (ny - 2) + 2 * (cap - 1);
@@ -99,13 +261,12 @@ __device__ __forceinline__ void sor_wavefront(double *Ps, const double *Cs, int 
                 const double n = Ps[rowc - PH + jh], so = Ps[rowc + PH + jh];
                 const double w = Po[jh], e = Po[jh + 1];
                 const double cp = Cs[rowc + jh];
-                const double d = fma(ca, n + so, fma(cb, e + w, fma(-beta, c, -cp)));
+                const double d = fma(k.ca, n + so, fma(k.cb, e + w, fma(-k.beta, c, -cp)));
                 Ps[rowc + jh] = c + d;
                 if (TRACK) {
-                    if (!(fabs(d) <= tol)) {
-                        if (s < 64) mask |= 1ull << s;
-                        else viol[s - 64] = 1;
-                    }
+                    const bool v = exceeds(d, k.tol);
+                    if (s < 64) mask |= (unsigned long long)v << s;
+                    else if (v) viol[s - 64] = 1;
                 }
             }
         }
@@ -113,20 +274,279 @@ __device__ __forceinline__ void sor_wavefront(double *Ps, const double *Cs, int 
     }
 }
 
-template <bool CP_SMEM>
-__global__ void __launch_bounds__(1024, 1) chorin_chip_kernel(const ChipArgs a) {
+struct SplitSor {
+    // smem: Ps [2*HS] | Cs [2*HS] (if CP_SMEM) | aux [2*nx] | viol
+    template <bool CP_SMEM>
+    static __device__ int run(const ChipArgs &a, double *smem, const double *un, const double *vn, double *pg,
+                              const Coef &k, int cap, int *viol, unsigned long long *s_mask, int *s_need) {
+        const int nx = a.g.nx, ny = a.g.ny, PH = a.PH, HS = a.HS;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        double *Ps = smem;
+        double *Cs = CP_SMEM ? smem + 2 * HS : a.cprime + (size_t)blockIdx.x * 2 * HS;
+        for (int i = warp; i < nx; i += nwarps)
+            for (int j = lane; j < ny; j += 32) {
+                const size_t q = (size_t)i * ny + j;
+                const int so = split_off(i, j, PH, HS);
+                Ps[so] = pg[q];
+                double c = 0.0;
+                if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1)
+                    c = k.cc * (k.cu * (un[q] - un[q - ny]) + k.cv * (vn[q] - vn[q - 1]));
+                Cs[so] = c;
+            }
+        __syncthreads();
+        int need = 0;
+        if (cap > 0) {
+            unsigned long long mask = 0ull;
+            sor_wavefront_split<true>(Ps, Cs, nx, ny, PH, HS, cap, k, mask, viol);
+            need = sweeps_needed(mask, cap, viol, s_mask, s_need);
+            if (need < cap) {
+                // the sequential loop would have stopped after `need` sweeps: redo from the
+                // untouched global p with the sweep count capped (rare: near steady state)
+                for (int i = warp; i < nx; i += nwarps)
+                    for (int j = lane; j < ny; j += 32) Ps[split_off(i, j, PH, HS)] = pg[(size_t)i * ny + j];
+                __syncthreads();
+                unsigned long long dummy = 0ull;
+                sor_wavefront_split<false>(Ps, Cs, nx, ny, PH, HS, need, k, dummy, viol);
+            }
+        }
+        for (int i = warp; i < nx; i += nwarps)
+            for (int j = lane; j < ny; j += 32) pg[(size_t)i * ny + j] = Ps[split_off(i, j, PH, HS)];
+        __syncthreads();
+        return need;
+    }
+};
+
+// ============================ REG implementation of phase B ====================================
+// Block Gauss-Seidel wavefront.  Each thread owns a BR x BC block of p in REGISTERS for the whole
+// solve.  One "super-stage" T = bi + bj + 2s lets every block (bi,bj) whose sweep index
+// s = (T - bi - bj)/2 is an integer in [0, cap) perform sweep s over ITS OWN cells, sequentially in
+// lexicographic order (fully unrolled, all operands in registers).  A block needs, at super-stage T,
+//   * the bottom row of block (bi-1,bj) and the right column of (bi,bj-1) after THEIR sweep s
+//     (done at T-1), and
+//   * the top row of (bi+1,bj) and the left column of (bi,bj+1) after their sweep s-1 (also T-1),
+// which is exactly what the lexicographic order of the reference gives every cell (new north/west,
+// old south/east), so the result is the sequential one.  Blocks active at the same T have the same
+// (bi+bj) parity and never touch, so there is ONE __syncthreads per super-stage and
+// (nbr+nbc-2) + 2*cap - 1 super-stages per solve (134 for 128x128, cap 49, instead of 347
+// cell-level stages).  The host orders threads by (parity, bi+bj) so that whole warps are
+// active / idle together.
+//
+// Shared memory, NT threads per CTA (compile time, so every offset is an immediate):
+//   H[slot][thread]: [0,BC) top row, [BC,2BC) bottom row, [2BC,2BC+BR) left column,
+//   [2BC+BR,2BC+2BR) right column of each block.  A thread reads its neighbour's facing slots;
+//   on a physical boundary nobody reads the thread's own facing slots, so those hold the frozen
+//   boundary values of p and are never republished: every halo read is H[slot*NT + some thread].
+//   C' as double2 chunks Cs[chunk][thread] in lexicographic cell order (conflict-free LDS.128).
+template <int BR, int BC>
+struct RegGeom {
+    static constexpr int NSLOT = 2 * BC + 2 * BR;
+    static constexpr int NCELL = BR * BC;
+    static constexpr int NCH = (NCELL + 1) / 2;       // double2 chunks of C'
+};
+
+struct RegHalo {
+    const double *hN, *hS, *hW, *hE;   // slot 0 of the facing row/column of the halo source
+    double *Hme;                       // H + tid
+    bool pubT, pubB, pubL, pubR;       // false on a physical boundary (slots hold boundary values)
+};
+
+template <int BR, int BC, int NT, bool WHOLE, bool TRACK>
+__device__ __forceinline__ bool reg_block_sweep(double (&P)[BR][BC], const double2 *__restrict__ Cme,
+                                                const RegHalo &h, int rows_live, int cols_live, const Coef &k) {
+    using G = RegGeom<BR, BC>;
+    double hn[BC], hs[BC], hw[BR], he[BR];
+#pragma unroll
+    for (int lj = 0; lj < BC; ++lj) { hn[lj] = h.hN[lj * NT]; hs[lj] = h.hS[lj * NT]; }
+#pragma unroll
+    for (int li = 0; li < BR; ++li) { hw[li] = h.hW[li * NT]; he[li] = h.hE[li * NT]; }
+    bool viol = false;
+#pragma unroll
+    for (int li = 0; li < BR; ++li) {
+#pragma unroll
+        for (int lj = 0; lj < BC; ++lj) {
+            constexpr int dummy = 0; (void)dummy;
+            const int q = li * BC + lj;
+            const double2 cc2 = Cme[(q >> 1) * NT];
+            const double cp = (q & 1) ? cc2.y : cc2.x;
+            const double n = li > 0 ? P[li - 1][lj] : hn[lj];          // new (this sweep)
+            const double w = lj > 0 ? P[li][lj - 1] : hw[li];          // new
+            const double s = li < BR - 1 ? P[li + 1][lj] : hs[lj];     // old (previous sweep)
+            const double e = lj < BC - 1 ? P[li][lj + 1] : he[li];     // old
+            const double c = P[li][lj];
+            // old operands first: the dependent chain through the freshly updated w and n is 2 FMAs + 1 add
+            const double z = fma(k.ca, s, fma(k.cb, e, fma(-k.beta, c, -cp)));
+            const double d = fma(k.ca, n, fma(k.cb, w, z));
+            if (WHOLE) {
+                P[li][lj] = c + d;
+                if (TRACK) viol |= exceeds(d, k.tol);
+            } else {
+                const bool live = li < rows_live && lj < cols_live;
+                P[li][lj] = live ? c + d : c;
+                if (TRACK) viol |= live && exceeds(d, k.tol);
+            }
+        }
+    }
+#pragma unroll
+    for (int lj = 0; lj < BC; ++lj) {
+        if (h.pubT) h.Hme[lj * NT] = P[0][lj];
+        if (h.pubB) h.Hme[(BC + lj) * NT] = P[BR - 1][lj];
+    }
+#pragma unroll
+    for (int li = 0; li < BR; ++li) {
+        if (h.pubL) h.Hme[(2 * BC + li) * NT] = P[li][0];
+        if (h.pubR) h.Hme[(2 * BC + BR + li) * NT] = P[li][BC - 1];
+    }
+    return viol;
+}
+
+template <int BR, int BC, int NT, bool TRACK>
+__device__ __forceinline__ void sor_wavefront_reg(double (&P)[BR][BC], const double2 *Cme, const RegHalo &h,
+                                                  bool owner, int bd, int tmax, int rows_live, int cols_live,
+                                                  int cap, const Coef &k, unsigned long long &mask) {
+    const bool whole = rows_live == BR && cols_live == BC;
+    // publish the whole perimeter once
+    if (owner) {
+#pragma unroll
+        for (int lj = 0; lj < BC; ++lj) {
+            if (h.pubT) h.Hme[lj * NT] = P[0][lj];
+            if (h.pubB) h.Hme[(BC + lj) * NT] = P[BR - 1][lj];
+        }
+#pragma unroll
+        for (int li = 0; li < BR; ++li) {
+            if (h.pubL) h.Hme[(2 * BC + li) * NT] = P[li][0];
+            if (h.pubR) h.Hme[(2 * BC + BR + li) * NT] = P[li][BC - 1];
+        }
+    }
+    __syncthreads();
+    for (int T = 0; T <= tmax; ++T) {
+        const int two_s = T - bd;
+        const bool work = owner && !(two_s & 1) && (unsigned)two_s <= (unsigned)(2 * (cap - 1));
+        if (__any_sync(0xffffffffu, work)) {
+            const bool all_whole = __all_sync(0xffffffffu, whole || !work);
+            if (work) {
+                bool v;
+                if (all_whole) v = reg_block_sweep<BR, BC, NT, true, TRACK>(P, Cme, h, rows_live, cols_live, k);
+                else v = reg_block_sweep<BR, BC, NT, false, TRACK>(P, Cme, h, rows_live, cols_live, k);
+                if (TRACK) mask |= (unsigned long long)v << (two_s >> 1);   // REG is planned for cap <= 64 only
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int BR, int BC, int NT>
+struct RegSor {
+    using G = RegGeom<BR, BC>;
+    // smem: Cs double2 [NCH*NT] | H [NSLOT*NT] | aux [2*nx] | viol
+    static constexpr size_t SMEM_DOUBLES = (size_t)2 * G::NCH * NT + (size_t)G::NSLOT * NT;
+
+    static __device__ int run(const ChipArgs &a, double *smem, const double *un, const double *vn, double *pg,
+                              const Coef &k, int cap, int *viol, unsigned long long *s_mask, int *s_need) {
+        const int nx = a.g.nx, ny = a.g.ny, tid = threadIdx.x;
+        double2 *Cs = reinterpret_cast<double2 *>(smem);
+        double *H = smem + (size_t)2 * G::NCH * NT;
+        const bool owner = tid < a.nblocks;
+        BlockDesc ds{1, 1, -1, -1, -1, -1, 0};
+        if (owner) ds = a.desc[tid];
+        const int r0 = ds.r0, c0 = ds.c0;
+        const int rows_live = min(BR, nx - 1 - r0), cols_live = min(BC, ny - 1 - c0);
+        RegHalo h;
+        h.Hme = H + tid;
+        h.pubT = ds.nN >= 0; h.pubB = ds.nS >= 0; h.pubL = ds.nW >= 0; h.pubR = ds.nE >= 0;
+        h.hN = h.pubT ? H + BC * NT + ds.nN : H + tid;                       // neighbour's bottom row / own top slots
+        h.hS = h.pubB ? H + ds.nS : H + BC * NT + tid;                       // neighbour's top row / own bottom slots
+        h.hW = h.pubL ? H + (2 * BC + BR) * NT + ds.nW : H + 2 * BC * NT + tid;   // neighbour's right col / own left
+        h.hE = h.pubR ? H + 2 * BC * NT + ds.nE : H + (2 * BC + BR) * NT + tid;   // neighbour's left col / own right
+        const double2 *Cme = Cs + tid;
+        double2 *Cw = Cs + tid;
+
+        auto pval = [&](int i, int j) { return (i >= 0 && i < nx && j >= 0 && j < ny) ? pg[(size_t)i * ny + j] : 0.0; };
+        if (owner) {
+            // frozen boundary values of p go into the (otherwise unread) own facing slots
+#pragma unroll
+            for (int lj = 0; lj < BC; ++lj) {
+                if (!h.pubT) h.Hme[lj * NT] = pval(r0 - 1, c0 + lj);
+                if (!h.pubB) h.Hme[(BC + lj) * NT] = pval(r0 + BR, c0 + lj);
+            }
+#pragma unroll
+            for (int li = 0; li < BR; ++li) {
+                if (!h.pubL) h.Hme[(2 * BC + li) * NT] = pval(r0 + li, c0 - 1);
+                if (!h.pubR) h.Hme[(2 * BC + BR + li) * NT] = pval(r0 + li, c0 + BC);
+            }
+            // C' of the owned cells as double2 chunks in lexicographic order
+            double hold = 0.0;
+#pragma unroll
+            for (int li = 0; li < BR; ++li)
+#pragma unroll
+                for (int lj = 0; lj < BC; ++lj) {
+                    const int i = r0 + li, j = c0 + lj, q = li * BC + lj;
+                    double c = 0.0;
+                    if (i < nx - 1 && j < ny - 1) {
+                        const size_t g = (size_t)i * ny + j;
+                        c = k.cc * (k.cu * (un[g] - un[g - ny]) + k.cv * (vn[g] - vn[g - 1]));
+                    }
+                    if (q & 1) Cw[(q >> 1) * NT] = make_double2(hold, c);
+                    else if (q == G::NCELL - 1) Cw[(q >> 1) * NT] = make_double2(c, 0.0);
+                    else hold = c;
+                }
+        }
+        double P[BR][BC];
+        auto load_block = [&]() {
+#pragma unroll
+            for (int li = 0; li < BR; ++li)
+#pragma unroll
+                for (int lj = 0; lj < BC; ++lj) {
+                    const int i = r0 + li, j = c0 + lj;
+                    P[li][lj] = (owner && i < nx && j < ny) ? pg[(size_t)i * ny + j] : 0.0;
+                }
+        };
+        load_block();
+        const int nbr = (nx - 2 + BR - 1) / BR, nbc = (ny - 2 + BC - 1) / BC;
+        int need = 0;
+        if (cap > 0) {
+            unsigned long long mask = 0ull;
+            sor_wavefront_reg<BR, BC, NT, true>(P, Cme, h, owner, ds.bd, nbr + nbc - 2 + 2 * (cap - 1), rows_live,
+                                                cols_live, cap, k, mask);
+            need = sweeps_needed(mask, cap, viol, s_mask, s_need);
+            if (need < cap) {
+                load_block();
+                unsigned long long dummy = 0ull;
+                sor_wavefront_reg<BR, BC, NT, false>(P, Cme, h, owner, ds.bd, nbr + nbc - 2 + 2 * (need - 1), rows_live,
+                                                     cols_live, need, k, dummy);
+            }
+        }
+        if (owner) {
+#pragma unroll
+            for (int li = 0; li < BR; ++li)
+#pragma unroll
+                for (int lj = 0; lj < BC; ++lj)
+                    if (li < rows_live && lj < cols_live) pg[(size_t)(r0 + li) * ny + c0 + lj] = P[li][lj];
+        }
+        __syncthreads();
+        return need;
+    }
+};
+
+// ================================== the fused step kernel =======================================
+// MODE 0: SPLIT with C' in smem, 1: SPLIT with C' in global, 2: REG<2,4,512>, 3: REG<7,6,384>,
+// 4: REG<2,4,256>
+template <int MODE>
+__device__ __forceinline__ void chorin_chip_body(const ChipArgs &a) {
     extern __shared__ double smem[];
     __shared__ unsigned long long s_mask;
     __shared__ int s_need;
 
-    const int nx = a.g.nx, ny = a.g.ny, PH = a.PH, HS = a.HS;
+    const int nx = a.g.nx, ny = a.g.ny;
     const size_t N = (size_t)nx * ny;
-    const int b = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int b = blockIdx.x, tid = threadIdx.x;
 
-    double *Ps = smem;
-    double *Cs = CP_SMEM ? smem + 2 * HS : a.cprime + (size_t)b * 2 * HS;
-    double *aux = smem + (CP_SMEM ? 4 : 2) * HS;           // 2*nx doubles (Thomas coefficients)
+    size_t used;
+    if constexpr (MODE == 0) used = (size_t)4 * a.HS;
+    else if constexpr (MODE == 1) used = (size_t)2 * a.HS;
+    else if constexpr (MODE == 2) used = RegSor<2, 4, 512>::SMEM_DOUBLES;
+    else if constexpr (MODE == 4) used = RegSor<2, 4, 256>::SMEM_DOUBLES;
+    else used = RegSor<7, 6, 384>::SMEM_DOUBLES;
+    double *aux = smem + used;                             // 2*nx doubles (Thomas coefficients)
     int *viol = reinterpret_cast<int *>(aux + 2 * nx);     // max(0, nit-65) ints
 
     const double dt = a.g.dt, dx = a.g.dx, dy = a.g.dy, rho = a.g.rho, beta = a.g.beta;
@@ -134,9 +554,10 @@ __global__ void __launch_bounds__(1024, 1) chorin_chip_kernel(const ChipArgs a) 
     const double *bcval = a.bcval ? a.bcval + (size_t)b * a.n_bcs : nullptr;
     const double dx2 = dx * dx, dy2 = dy * dy;
     const double den = 2.0 * dx2 + 2.0 * dy2;
-    const double ca = beta * dy2 / den, cb = beta * dx2 / den, cc = beta / den;
-    const double cu = dx * rho * dy2 / dt, cv = dy * rho * dx2 / dt;
-    const double r2dx = 1.0 / (2.0 * dx), r2dy = 1.0 / (2.0 * dy), rdx2 = 1.0 / dx2, rdy2 = 1.0 / dy2;
+    Coef k;
+    k.ca = beta * dy2 / den; k.cb = beta * dx2 / den; k.cc = beta / den;
+    k.cu = dx * rho * dy2 / dt; k.cv = dy * rho * dx2 / dt;
+    k.beta = beta; k.tol = a.g.tol;
     const int cap = a.g.nit - 1;
 
     int cur = 0, prev = 1, nxt = 2;
@@ -147,183 +568,22 @@ __global__ void __launch_bounds__(1024, 1) chorin_chip_kernel(const ChipArgs a) 
         const double *up = a.bufU[prev] + (size_t)b * N, *vp = a.bufV[prev] + (size_t)b * N;
         double *un = a.bufU[nxt] + (size_t)b * N, *vn = a.bufV[nxt] + (size_t)b * N;
 
-        // ------------------------------ phase A: predictor + u/v BCs --------------------
-        if (a.phases & 1) {
-            if (a.g.method == NNS_METHOD_EXPLICIT) {
-                for (int i = warp; i < nx; i += nwarps)
-                    for (int j = lane; j < ny; j += 32) {
-                        const size_t q = (size_t)i * ny + j;
-                        const double u0 = uc[q], v0 = vc[q];
-                        double ru = u0, rv = v0;
-                        if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1) {
-                            const double u1c = up[q], v1c = vp[q];
-                            const double uS = uc[q + ny], uN = uc[q - ny], uE = uc[q + 1], uW = uc[q - 1];
-                            const double vS = vc[q + ny], vN = vc[q - ny], vE = vc[q + 1], vW = vc[q - 1];
-                            const double pS = up[q + ny], pN = up[q - ny], pE = up[q + 1], pW = up[q - 1];
-                            const double qS = vp[q + ny], qN = vp[q - ny], qE = vp[q + 1], qW = vp[q - 1];
-                            // both advection terms difference along axis 0 (chorin_fd:74,76,83,85)
-                            const double k0 = u0 * r2dx + v0 * r2dy, k1 = u1c * r2dx + v1c * r2dy;
-                            const double advu = 1.5 * (k0 * (uS - uN)) - 0.5 * (k1 * (pS - pN));
-                            const double advv = 1.5 * (k0 * (vS - vN)) - 0.5 * (k1 * (qS - qN));
-                            const double lapu = 1.5 * ((uS - 2.0 * u0 + uN) * rdx2 + (uE - 2.0 * u0 + uW) * rdy2) -
-                                                0.5 * ((pS - 2.0 * u1c + pN) * rdx2 + (pE - 2.0 * u1c + pW) * rdy2);
-                            const double lapv = 1.5 * ((vS - 2.0 * v0 + vN) * rdx2 + (vE - 2.0 * v0 + vW) * rdy2) -
-                                                0.5 * ((qS - 2.0 * v1c + qN) * rdx2 + (qE - 2.0 * v1c + qW) * rdy2);
-                            ru = u0 - dt * advu + (dt * nu) * lapu;
-                            rv = v0 - dt * advv + (dt * nu) * lapv;
-                        }
-                        un[q] = ru;
-                        vn[q] = rv;
-                    }
-                __syncthreads();
-            } else {
-                // semi-implicit: AB2 advection + Crank-Nicolson ADI, all four solves along axis 0
-                // (chorin_fd:93-167; diagonal (2/nu)dx^2+2dt :108, vC scaled by dx^2 :150).
-                const double kx = 2.0 / nu * dx2, ky = 2.0 / nu * dy2;
-                // stage 1 right-hand sides uC, vC -> un, vn interiors (edges = copies of u^n)
-                for (int i = warp; i < nx; i += nwarps)
-                    for (int j = lane; j < ny; j += 32) {
-                        const size_t q = (size_t)i * ny + j;
-                        const double u0 = uc[q], v0 = vc[q];
-                        double ru = u0, rv = v0;
-                        if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1) {
-                            const double u1c = up[q], v1c = vp[q];
-                            const double uS = uc[q + ny], uN = uc[q - ny], uE = uc[q + 1], uW = uc[q - 1];
-                            const double vS = vc[q + ny], vN = vc[q - ny], vE = vc[q + 1], vW = vc[q - 1];
-                            const double pS = up[q + ny], pN = up[q - ny], pE = up[q + 1], pW = up[q - 1];
-                            const double qS = vp[q + ny], qN = vp[q - ny], qE = vp[q + 1], qW = vp[q - 1];
-                            const double uHn = u0 * (uS - uN) * r2dx + v0 * (uE - uW) * r2dy;
-                            const double uHn1 = u1c * (pS - pN) * r2dx + v1c * (pE - pW) * r2dy;
-                            const double vHn = u0 * (vS - vN) * r2dx + v0 * (vE - vW) * r2dy;
-                            const double vHn1 = u1c * (qS - qN) * r2dx + v1c * (qE - qW) * r2dy;
-                            const double uC2 = dt * nu * ((uS - 2.0 * u0 + uN) * rdx2 + (uE - 2.0 * u0 + uW) * rdy2);
-                            const double vC2 = dt * nu * ((vS - 2.0 * v0 + vN) * rdx2 + (vE - 2.0 * v0 + vW) * rdy2);
-                            ru = kx * (0.5 * dt * (3.0 * uHn - uHn1) + uC2);
-                            rv = kx * (0.5 * dt * (3.0 * vHn - vHn1) + vC2);
-                        }
-                        un[q] = ru;
-                        vn[q] = rv;
-                    }
-                __syncthreads();
-                cta_thomas_axis0(un, nx, ny, kx + 2.0 * dt, -dt, aux);   // ut
-                cta_thomas_axis0(vn, nx, ny, kx + 2.0 * dt, -dt, aux);   // vt
-                // stage 2 right-hand sides uS, vS (in place on the interiors)
-                for (int i = 1 + warp; i < nx - 1; i += nwarps)
-                    for (int j = 1 + lane; j < ny - 1; j += 32) {
-                        const size_t q = (size_t)i * ny + j;
-                        const double u0 = uc[q], v0 = vc[q];
-                        un[q] = ky * (un[q] + u0) - dt * (uc[q + 1] - 2.0 * u0 + uc[q - 1]);
-                        vn[q] = ky * (vn[q] + v0) - dt * (vc[q + 1] - 2.0 * v0 + vc[q - 1]);
-                    }
-                __syncthreads();
-                cta_thomas_axis0(un, nx, ny, ky + 2.0 * dt, -dt, aux);   // B is applied along axis 0 (:159)
-                cta_thomas_axis0(vn, nx, ny, ky + 2.0 * dt, -dt, aux);
-            }
-            cta_apply_bc_global(un, nx, ny, a.ubc, bcval, dx, dy);
-            cta_apply_bc_global(vn, nx, ny, a.vbc, bcval, dx, dy);
-        }
+        if (a.phases & 1) phase_predictor(a, uc, vc, up, vp, un, vn, nu, bcval, aux);
 
-        // ------------------------------ phase B: SOR pressure ----------------------------
-        int need = 0;
         if (a.phases & 2) {
             if (tid == 0) s_mask = 0ull;
-            for (int k = tid; k < cap - 64; k += blockDim.x) viol[k] = 0;
-            for (int i = warp; i < nx; i += nwarps)
-                for (int j = lane; j < ny; j += 32) {
-                    const size_t q = (size_t)i * ny + j;
-                    const int so = split_off(i, j, PH, HS);
-                    Ps[so] = pg[q];
-                    double c = 0.0;
-                    if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1)
-                        c = cc * (cu * (un[q] - un[q - ny]) + cv * (vn[q] - vn[q - 1]));
-                    Cs[so] = c;
-                }
+            for (int q = tid; q < cap - 64; q += blockDim.x) viol[q] = 0;
             __syncthreads();
-            need = cap > 0 ? cap : 0;
-            if (cap > 0) {
-                unsigned long long mask = 0ull;
-                sor_wavefront<true>(Ps, Cs, nx, ny, PH, HS, cap, ca, cb, beta, a.g.tol, mask, viol);
-                unsigned lo = (unsigned)mask, hi = (unsigned)(mask >> 32);
-                lo = __reduce_or_sync(0xffffffffu, lo);
-                hi = __reduce_or_sync(0xffffffffu, hi);
-                if (lane == 0) atomicOr(&s_mask, ((unsigned long long)hi << 32) | lo);
-                __syncthreads();
-                if (tid == 0) {
-                    int nd = cap;
-                    const int c64 = cap < 64 ? cap : 64;
-                    const unsigned long long full = c64 == 64 ? ~0ull : ((1ull << c64) - 1ull);
-                    const unsigned long long clr = ~s_mask & full;
-                    if (clr) nd = __ffsll((long long)clr);      // first sweep s with max|dp| <= tol: s+1 sweeps run
-                    else
-                        for (int s = 64; s < cap; ++s)
-                            if (!viol[s - 64]) { nd = s + 1; break; }
-                    s_need = nd;
-                }
-                __syncthreads();
-                need = s_need;
-                if (need < cap) {
-                    // the sequential loop would have stopped after `need` sweeps: redo from the
-                    // untouched global p with the sweep count capped (rare: near steady state)
-                    for (int i = warp; i < nx; i += nwarps)
-                        for (int j = lane; j < ny; j += 32)
-                            Ps[split_off(i, j, PH, HS)] = pg[(size_t)i * ny + j];
-                    __syncthreads();
-                    unsigned long long dummy = 0ull;
-                    sor_wavefront<false>(Ps, Cs, nx, ny, PH, HS, need, ca, cb, beta, a.g.tol, dummy, viol);
-                }
-            }
+            int need;
+            if constexpr (MODE == 0) need = SplitSor::run<true>(a, smem, un, vn, pg, k, cap, viol, &s_mask, &s_need);
+            else if constexpr (MODE == 1) need = SplitSor::run<false>(a, smem, un, vn, pg, k, cap, viol, &s_mask, &s_need);
+            else if constexpr (MODE == 2) need = RegSor<2, 4, 512>::run(a, smem, un, vn, pg, k, cap, viol, &s_mask, &s_need);
+            else if constexpr (MODE == 4) need = RegSor<2, 4, 256>::run(a, smem, un, vn, pg, k, cap, viol, &s_mask, &s_need);
+            else need = RegSor<7, 6, 384>::run(a, smem, un, vn, pg, k, cap, viol, &s_mask, &s_need);
             if (a.sweeps && tid == 0) a.sweeps[(size_t)(a.step0 + n) * a.g.batch + b] = need;
-        } else if (a.phases & 4) {
-            for (int i = warp; i < nx; i += nwarps)
-                for (int j = lane; j < ny; j += 32) Ps[split_off(i, j, PH, HS)] = pg[(size_t)i * ny + j];
-            __syncthreads();
         }
 
-        // ------------------------------ phase C: p BCs, projection, snapshot --------------
-        if (a.phases & 4) {
-            for (int k = 0; k < a.pbc.n; ++k) {
-                const double g = bcval ? bcval[a.pbc.slot[k]] : a.pbc.value[k];
-                const int side = a.pbc.side[k];
-                const bool neu = a.pbc.type[k] == NNS_BC_NEUMANN;
-                if (side == NNS_SIDE_LEFT || side == NNS_SIDE_RIGHT) {
-                    const int i = side == NNS_SIDE_LEFT ? 0 : nx - 1, in = side == NNS_SIDE_LEFT ? 1 : nx - 2;
-                    const double sg = side == NNS_SIDE_LEFT ? -dx : dx;
-                    for (int j = tid; j < ny; j += blockDim.x)
-                        Ps[split_off(i, j, PH, HS)] = neu ? Ps[split_off(in, j, PH, HS)] + sg * g : g;
-                } else {
-                    const int j = side == NNS_SIDE_BOTTOM ? 0 : ny - 1, jn = side == NNS_SIDE_BOTTOM ? 1 : ny - 2;
-                    const double sg = side == NNS_SIDE_BOTTOM ? -dy : dy;
-                    for (int i = tid; i < nx; i += blockDim.x)
-                        Ps[split_off(i, j, PH, HS)] = neu ? Ps[split_off(i, jn, PH, HS)] + sg * g : g;
-                }
-                __syncthreads();
-            }
-        }
-        if (a.phases & 6) {
-            const size_t toff = ((size_t)b * a.nsteps_total + (a.step0 + n)) * N;
-            const double kx = dt / (2.0 * dx), ky = dt / (2.0 * dy);
-            unsigned long long bad = 0;
-            for (int i = warp; i < nx; i += nwarps)
-                for (int j = lane; j < ny; j += 32) {
-                    const size_t q = (size_t)i * ny + j;
-                    const double pc = Ps[split_off(i, j, PH, HS)];
-                    pg[q] = pc;
-                    if (a.traj_p) a.traj_p[toff + q] = pc;
-                    if (a.phases & 4) {
-                        double ru = un[q], rv = vn[q];
-                        if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1) {
-                            ru -= kx * (Ps[split_off(i + 1, j, PH, HS)] - Ps[split_off(i - 1, j, PH, HS)]);
-                            rv -= ky * (Ps[split_off(i, j + 1, PH, HS)] - Ps[split_off(i, j - 1, PH, HS)]);
-                            un[q] = ru;
-                            vn[q] = rv;
-                        }
-                        if (a.traj_u) a.traj_u[toff + q] = ru;
-                        if (a.traj_v) a.traj_v[toff + q] = rv;
-                        if (a.flags & NNS_FLAG_CHECK_FINITE) bad += !(isfinite(ru) && isfinite(rv) && isfinite(pc));
-                    }
-                }
-            if ((a.flags & NNS_FLAG_CHECK_FINITE) && bad) atomicAdd(a.nonfinite, bad);
-        }
+        if (a.phases & 6) phase_finish(a, pg, un, vn, bcval, ((size_t)b * a.nsteps_total + (a.step0 + n)) * N);
         __syncthreads();
         const int t = prev; prev = cur; cur = nxt; nxt = t;
     }
@@ -344,18 +604,82 @@ __global__ void __launch_bounds__(1024, 1) chorin_chip_kernel(const ChipArgs a) 
     }
 }
 
+template <int MODE, int NTMAX>
+__global__ void __launch_bounds__(NTMAX, 1) chorin_chip_kernel(const ChipArgs a) {
+    chorin_chip_body<MODE>(a);
+}
+
+// REG<7,6>: 126 = 18*7 = 21*6, so a 128x128 grid is 378 blocks with no ragged edge.  384 threads =
+// 3 warps per SM sub-partition -> 168 registers per thread (84 of them hold p).
+__global__ void __maxnreg__(168) chorin_chip_kernel_reg76(const ChipArgs a) { chorin_chip_body<3>(a); }
+
 // ---- host side ---------------------------------------------------------------------------
 
 struct ChipPlan {
-    int PH, HS, threads;
+    int mode;            // see chorin_chip_kernel
+    int PH, HS, threads, nblocks;
     size_t smem_bytes;
-    bool cp_smem;
     bool fits;
+    std::vector<BlockDesc> desc;
 };
+
+static bool plan_reg(const nns_handle *h, int BR, int BC, int nt, size_t per_thread_doubles, ChipPlan &pl) {
+    const int nx = h->g.nx, ny = h->g.ny;
+    const int nbr = (nx - 2 + BR - 1) / BR, nbc = (ny - 2 + BC - 1) / BC;
+    const int nb = nbr * nbc;
+    if (nb > nt || nx > 32000 || ny > 32000) return false;
+    const size_t extra = sizeof(double) * 2 * nx + sizeof(int) * (size_t)(h->g.nit > 65 ? h->g.nit - 65 : 0) + 64;
+    const size_t bytes = sizeof(double) * per_thread_doubles * nt + extra;
+    if (bytes > (size_t)h->max_smem_optin) return false;
+    // order the blocks by anti-diagonal so that a warp's blocks enter / leave the band together
+    struct Item { int key, bi, bj; };
+    std::vector<Item> items;
+    for (int bi = 0; bi < nbr; ++bi)
+        for (int bj = 0; bj < nbc; ++bj) items.push_back({bi + bj, bi, bj});
+    std::stable_sort(items.begin(), items.end(), [](const Item &x, const Item &y) {
+        if ((x.key & 1) != (y.key & 1)) return (x.key & 1) < (y.key & 1);   // blocks of one parity work together
+        return x.key != y.key ? x.key < y.key : x.bj < y.bj;
+    });
+    std::vector<int> tid_of((size_t)nb);
+    for (int t = 0; t < nb; ++t) tid_of[(size_t)items[t].bi * nbc + items[t].bj] = t;
+    pl.desc.resize(nb);
+    for (int t = 0; t < nb; ++t) {
+        const int bi = items[t].bi, bj = items[t].bj;
+        BlockDesc d;
+        d.r0 = (short)(1 + BR * bi);
+        d.c0 = (short)(1 + BC * bj);
+        d.nN = bi > 0 ? (short)tid_of[(size_t)(bi - 1) * nbc + bj] : (short)-1;
+        d.nS = bi < nbr - 1 ? (short)tid_of[(size_t)(bi + 1) * nbc + bj] : (short)-1;
+        d.nW = bj > 0 ? (short)tid_of[(size_t)bi * nbc + bj - 1] : (short)-1;
+        d.nE = bj < nbc - 1 ? (short)tid_of[(size_t)bi * nbc + bj + 1] : (short)-1;
+        d.bd = (short)(bi + bj);
+        pl.desc[t] = d;
+    }
+    pl.threads = nt;
+    pl.nblocks = nb;
+    pl.smem_bytes = bytes;
+    pl.fits = true;
+    return true;
+}
+
+static int forced_mode() {
+    const char *e = getenv("NNS_CHIP_MODE");    // "split" forces the generic path (tests exercise both)
+    if (e && !strcmp(e, "split")) return 0;
+    if (e && !strcmp(e, "reg24")) return 2;
+    if (e && !strcmp(e, "reg76")) return 3;
+    return -1;
+}
 
 ChipPlan chorin_chip_plan(const nns_handle *h) {
     ChipPlan pl{};
     const int nx = h->g.nx, ny = h->g.ny;
+    const int force = forced_mode();
+    if (force != 0 && h->g.nit <= 65) {      // REG keeps the per-sweep exit flags in one 64-bit mask
+        // doubles per thread: C' (2*NCH) + halo slots: RegSor<2,4>: 8 + 12; RegSor<7,6>: 42 + 26
+        if ((force < 0 || force == 2) && plan_reg(h, 2, 4, 256, 8 + 12, pl)) { pl.mode = 4; return pl; }
+        if ((force < 0 || force == 2) && plan_reg(h, 2, 4, 512, 8 + 12, pl)) { pl.mode = 2; return pl; }
+        if ((force < 0 || force == 3) && plan_reg(h, 7, 6, 384, 42 + 26, pl)) { pl.mode = 3; return pl; }
+    }
     pl.PH = (ny + 1) / 2;
     int hs = nx * pl.PH;
     hs = ((hs + 15) / 16) * 16 + 8;          // half stride = 8 mod 16 doubles: the halves sit 16 banks apart
@@ -363,16 +687,26 @@ ChipPlan chorin_chip_plan(const nns_handle *h) {
     const size_t extra = sizeof(double) * 2 * nx + sizeof(int) * (size_t)(h->g.nit > 65 ? h->g.nit - 65 : 0) + 64;
     const size_t one = sizeof(double) * 2 * (size_t)hs;
     const size_t lim = (size_t)h->max_smem_optin;
-    pl.cp_smem = 2 * one + extra <= lim;
-    pl.smem_bytes = (pl.cp_smem ? 2 : 1) * one + extra;
+    const bool cp_smem = 2 * one + extra <= lim;
+    pl.mode = cp_smem ? 0 : 1;
+    pl.smem_bytes = (cp_smem ? 2 : 1) * one + extra;
     pl.fits = pl.smem_bytes <= lim;
     const long cells = (long)nx * ny;
     pl.threads = cells >= 8192 ? 1024 : cells >= 1024 ? 512 : 256;
     return pl;
 }
 
+template <int MODE, int NTMAX>
+static int launch_mode(const ChipPlan &pl, const ChipArgs &a, int count, cudaStream_t st) {
+    NNS_CUDA(cudaFuncSetAttribute(chorin_chip_kernel<MODE, NTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pl.smem_bytes));
+    chorin_chip_kernel<MODE, NTMAX><<<count, pl.threads, pl.smem_bytes, st>>>(a);
+    return NNS_OK;
+}
+
 int chorin_chip_launch(nns_handle *h, ChipArgs &a, cudaStream_t st, int m0, int count) {
-    const ChipPlan pl = chorin_chip_plan(h);
+    if (!h->chip_plan) h->chip_plan = new ChipPlan(chorin_chip_plan(h));
+    const ChipPlan &pl = *static_cast<const ChipPlan *>(h->chip_plan);
     if (!pl.fits) {
         set_error("chorin_fd chip path: grid %dx%d needs %zu B of shared memory (> %d)", h->g.nx, h->g.ny,
                   pl.smem_bytes, h->max_smem_optin);
@@ -380,24 +714,47 @@ int chorin_chip_launch(nns_handle *h, ChipArgs &a, cudaStream_t st, int m0, int 
     }
     a.PH = pl.PH;
     a.HS = pl.HS;
-    if (!pl.cp_smem && !h->d_cprime)
+    a.nblocks = pl.nblocks;
+    a.desc = nullptr;
+    if (pl.mode >= 2) {
+        if (!h->d_blockdesc) {
+            NNS_CUDA(cudaMalloc(&h->d_blockdesc, sizeof(BlockDesc) * pl.desc.size()));
+            NNS_CUDA(cudaMemcpy(h->d_blockdesc, pl.desc.data(), sizeof(BlockDesc) * pl.desc.size(),
+                                cudaMemcpyHostToDevice));
+        }
+        a.desc = static_cast<const BlockDesc *>(h->d_blockdesc);
+    }
+    if (pl.mode == 1 && !h->d_cprime)
         NNS_CUDA(cudaMalloc(&h->d_cprime, sizeof(double) * 2 * (size_t)pl.HS * h->g.batch));
     a.cprime = h->d_cprime ? h->d_cprime + (size_t)m0 * 2 * pl.HS : nullptr;
-    if (pl.cp_smem) {
-        NNS_CUDA(cudaFuncSetAttribute(chorin_chip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)pl.smem_bytes));
-        chorin_chip_kernel<true><<<count, pl.threads, pl.smem_bytes, st>>>(a);
-    } else {
-        NNS_CUDA(cudaFuncSetAttribute(chorin_chip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)pl.smem_bytes));
-        chorin_chip_kernel<false><<<count, pl.threads, pl.smem_bytes, st>>>(a);
+    int rc;
+    switch (pl.mode) {
+        case 0: rc = launch_mode<0, 1024>(pl, a, count, st); break;
+        case 1: rc = launch_mode<1, 1024>(pl, a, count, st); break;
+        case 2: rc = launch_mode<2, 512>(pl, a, count, st); break;
+        case 4: rc = launch_mode<4, 256>(pl, a, count, st); break;
+        default:
+            NNS_CUDA(cudaFuncSetAttribute(chorin_chip_kernel_reg76, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)pl.smem_bytes));
+            chorin_chip_kernel_reg76<<<count, pl.threads, pl.smem_bytes, st>>>(a);
+            rc = NNS_OK;
+            break;
     }
+    if (rc != NNS_OK) return rc;
     NNS_CUDA(cudaGetLastError());
     h->launches += 1;
     return NNS_OK;
 }
 
-bool chorin_chip_fits(const nns_handle *h) { return chorin_chip_plan(h).fits; }
+void chorin_chip_free_plan(nns_handle *h) {
+    delete static_cast<ChipPlan *>(h->chip_plan);
+    h->chip_plan = nullptr;
+}
+
+bool chorin_chip_fits(const nns_handle *h) {
+    if (h->chip_plan) return static_cast<const ChipPlan *>(h->chip_plan)->fits;
+    return chorin_chip_plan(h).fits;
+}
 
 int chorin_chip_run(nns_handle *h, double *bufU[3], double *bufV[3], double *p, int nsteps, int nsteps_total,
                     int step0, int phases, int fixup, double *tu, double *tv, double *tp, int32_t *sweeps,

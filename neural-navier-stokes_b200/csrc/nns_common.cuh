@@ -38,6 +38,8 @@ struct nns_handle {
     double *d_scratch[4];     // rotation / ui,vi workspace, [batch][nx][ny] each, lazily allocated
     double *d_stage[7];       // device staging of the host-buffer entry points
     cudaStream_t streams[4];  // copy/compute pipelining of the host-buffer entry points
+    void *chip_plan;          // chorin_fd chip path: cached ChipPlan (host) and block table (device)
+    void *d_blockdesc;
     double *d_cprime;         // SOR right-hand side when it does not fit in shared memory
     double *d_b;              // direct_fd rhs / second p buffer
     double *d_p2;

@@ -11,6 +11,17 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-10
 
 
+@pytest.fixture(autouse=True, params=["auto", "split"])
+def chip_mode(request, monkeypatch):
+    """Every test runs twice: with the planner's choice (register-block SOR where a template
+    instance fits) and with the generic split-row shared-memory SOR forced."""
+    if request.param == "auto":
+        monkeypatch.delenv("NNS_CHIP_MODE", raising=False)
+    else:
+        monkeypatch.setenv("NNS_CHIP_MODE", request.param)
+    return request.param
+
+
 def _params(g, key):
     return json.loads(str(g[key]))
 
