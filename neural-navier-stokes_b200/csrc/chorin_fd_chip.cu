@@ -48,6 +48,7 @@ struct ChipArgs {
     int PH, HS;              // SPLIT: half-row pitch, half-array stride (doubles)
     int nblocks;             // REG: number of blocks (threads that own cells)
     const BlockDesc *desc;   // REG
+    const short *tidmap;     // REG: thread id of block (bi, bj) at [bi * nbc + bj]
     int nsteps, nsteps_total, step0;
     int phases;              // bit0 A, bit1 B, bit2 C
     int fixup;               // copy final cur/prev into buffers 0/1
@@ -113,6 +114,7 @@ __device__ void phase_predictor(const ChipArgs &a, const double *uc, const doubl
     const double r2dx = 1.0 / (2.0 * dx), r2dy = 1.0 / (2.0 * dy), rdx2 = 1.0 / dx2, rdy2 = 1.0 / dy2;
     if (a.g.method == NNS_METHOD_EXPLICIT) {
         for (int i = warp; i < nx; i += nwarps)
+#pragma unroll 4
             for (int j = lane; j < ny; j += 32) {
                 const size_t q = (size_t)i * ny + j;
                 const double u0 = uc[q], v0 = vc[q];
@@ -195,6 +197,7 @@ __device__ void phase_finish(const ChipArgs &a, double *pg, double *un, double *
     const double kx = dt / (2.0 * dx), ky = dt / (2.0 * dy);
     unsigned long long bad = 0;
     for (int i = warp; i < nx; i += nwarps)
+#pragma unroll 4
         for (int j = lane; j < ny; j += 32) {
             const size_t q = (size_t)i * ny + j;
             const double pc = pg[q];
@@ -458,8 +461,43 @@ struct RegSor {
         h.hW = h.pubL ? H + (2 * BC + BR) * NT + ds.nW : H + 2 * BC * NT + tid;   // neighbour's right col / own left
         h.hE = h.pubR ? H + 2 * BC * NT + ds.nE : H + (2 * BC + BR) * NT + tid;   // neighbour's left col / own right
         const double2 *Cme = Cs + tid;
-        double2 *Cw = Cs + tid;
 
+        const int nbr = (nx - 2 + BR - 1) / BR, nbc = (ny - 2 + BC - 1) / BC;
+        const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+        double *Cd = smem;                    // the C' area viewed as doubles: cell q of thread t at ((q>>1)*NT + t)*2 + (q&1)
+        // Cooperative, coalesced pass over the rows of the grid; every value is scattered into the
+        // owning thread's private chunk.  (Per-thread block loads touch 32 different sectors per
+        // warp instruction and cost 4x more L1 cycles than the whole SOR setup should.)
+        auto scatter = [&](auto f) {
+            const int iend = min(nx, 1 + nbr * BR), jend = min(ny, 1 + nbc * BC);
+            for (int i = 1 + warp; i < iend; i += nwarps) {
+                const int bi = (i - 1) / BR, li = (i - 1) - bi * BR;
+                for (int j = 1 + lane; j < jend; j += 32) {
+                    const int bj = (j - 1) / BC, lj = (j - 1) - bj * BC;
+                    const int t = a.tidmap[bi * nbc + bj], q = li * BC + lj;
+                    Cd[((size_t)(q >> 1) * NT + t) * 2 + (q & 1)] = f(i, j);
+                }
+            }
+        };
+        double P[BR][BC];
+        auto take_block = [&]() {             // own chunks -> registers
+#pragma unroll
+            for (int c = 0; c < G::NCH; ++c) {
+                const double2 v = Cme[c * NT];
+                if (2 * c < G::NCELL) P[(2 * c) / BC][(2 * c) % BC] = v.x;
+                if (2 * c + 1 < G::NCELL) P[(2 * c + 1) / BC][(2 * c + 1) % BC] = v.y;
+            }
+        };
+        auto load_block = [&]() {             // direct (uncoalesced) loads: only used by the rare redo path
+#pragma unroll
+            for (int li = 0; li < BR; ++li)
+#pragma unroll
+                for (int lj = 0; lj < BC; ++lj) {
+                    const int i = r0 + li, j = c0 + lj;
+                    P[li][lj] = (owner && i < nx && j < ny) ? pg[(size_t)i * ny + j] : 0.0;
+                }
+        };
+        scatter([&](int i, int j) { return pg[(size_t)i * ny + j]; });
         auto pval = [&](int i, int j) { return (i >= 0 && i < nx && j >= 0 && j < ny) ? pg[(size_t)i * ny + j] : 0.0; };
         if (owner) {
             // frozen boundary values of p go into the (otherwise unread) own facing slots
@@ -473,35 +511,18 @@ struct RegSor {
                 if (!h.pubL) h.Hme[(2 * BC + li) * NT] = pval(r0 + li, c0 - 1);
                 if (!h.pubR) h.Hme[(2 * BC + BR + li) * NT] = pval(r0 + li, c0 + BC);
             }
-            // C' of the owned cells as double2 chunks in lexicographic order
-            double hold = 0.0;
-#pragma unroll
-            for (int li = 0; li < BR; ++li)
-#pragma unroll
-                for (int lj = 0; lj < BC; ++lj) {
-                    const int i = r0 + li, j = c0 + lj, q = li * BC + lj;
-                    double c = 0.0;
-                    if (i < nx - 1 && j < ny - 1) {
-                        const size_t g = (size_t)i * ny + j;
-                        c = k.cc * (k.cu * (un[g] - un[g - ny]) + k.cv * (vn[g] - vn[g - 1]));
-                    }
-                    if (q & 1) Cw[(q >> 1) * NT] = make_double2(hold, c);
-                    else if (q == G::NCELL - 1) Cw[(q >> 1) * NT] = make_double2(c, 0.0);
-                    else hold = c;
-                }
         }
-        double P[BR][BC];
-        auto load_block = [&]() {
-#pragma unroll
-            for (int li = 0; li < BR; ++li)
-#pragma unroll
-                for (int lj = 0; lj < BC; ++lj) {
-                    const int i = r0 + li, j = c0 + lj;
-                    P[li][lj] = (owner && i < nx && j < ny) ? pg[(size_t)i * ny + j] : 0.0;
-                }
-        };
-        load_block();
-        const int nbr = (nx - 2 + BR - 1) / BR, nbc = (ny - 2 + BC - 1) / BC;
+        __syncthreads();
+        take_block();
+        __syncthreads();
+        scatter([&](int i, int j) {
+            double c = 0.0;
+            if (i < nx - 1 && j < ny - 1) {
+                const size_t g = (size_t)i * ny + j;
+                c = k.cc * (k.cu * (un[g] - un[g - ny]) + k.cv * (vn[g] - vn[g - 1]));
+            }
+            return c;
+        });
         int need = 0;
         if (cap > 0) {
             unsigned long long mask = 0ull;
@@ -515,12 +536,26 @@ struct RegSor {
                                                      cols_live, need, k, dummy);
             }
         }
-        if (owner) {
+        // registers -> own chunks -> coalesced stores of the interior of p
+        __syncthreads();                      // C' (and, with cap == 0, its scatter) is dead from here on
+        {
+            double2 *Cw = Cs + tid;
 #pragma unroll
-            for (int li = 0; li < BR; ++li)
-#pragma unroll
-                for (int lj = 0; lj < BC; ++lj)
-                    if (li < rows_live && lj < cols_live) pg[(size_t)(r0 + li) * ny + c0 + lj] = P[li][lj];
+            for (int c = 0; c < G::NCH; ++c) {
+                double2 v;
+                v.x = P[(2 * c) / BC][(2 * c) % BC];
+                v.y = (2 * c + 1 < G::NCELL) ? P[(2 * c + 1) / BC][(2 * c + 1) % BC] : 0.0;
+                Cw[c * NT] = v;
+            }
+        }
+        __syncthreads();
+        for (int i = 1 + warp; i < nx - 1; i += nwarps) {
+            const int bi = (i - 1) / BR, li = (i - 1) - bi * BR;
+            for (int j = 1 + lane; j < ny - 1; j += 32) {
+                const int bj = (j - 1) / BC, lj = (j - 1) - bj * BC;
+                const int t = a.tidmap[bi * nbc + bj], q = li * BC + lj;
+                pg[(size_t)i * ny + j] = Cd[((size_t)(q >> 1) * NT + t) * 2 + (q & 1)];
+            }
         }
         __syncthreads();
         return need;
@@ -621,6 +656,7 @@ struct ChipPlan {
     size_t smem_bytes;
     bool fits;
     std::vector<BlockDesc> desc;
+    std::vector<short> tidmap;
 };
 
 static bool plan_reg(const nns_handle *h, int BR, int BC, int nt, size_t per_thread_doubles, ChipPlan &pl) {
@@ -643,6 +679,8 @@ static bool plan_reg(const nns_handle *h, int BR, int BC, int nt, size_t per_thr
     std::vector<int> tid_of((size_t)nb);
     for (int t = 0; t < nb; ++t) tid_of[(size_t)items[t].bi * nbc + items[t].bj] = t;
     pl.desc.resize(nb);
+    pl.tidmap.resize(nb);
+    for (int t = 0; t < nb; ++t) pl.tidmap[t] = (short)tid_of[t];
     for (int t = 0; t < nb; ++t) {
         const int bi = items[t].bi, bj = items[t].bj;
         BlockDesc d;
@@ -717,12 +755,15 @@ int chorin_chip_launch(nns_handle *h, ChipArgs &a, cudaStream_t st, int m0, int 
     a.nblocks = pl.nblocks;
     a.desc = nullptr;
     if (pl.mode >= 2) {
+        const size_t dbytes = sizeof(BlockDesc) * pl.desc.size();     // block table, then the (bi,bj) -> tid map
         if (!h->d_blockdesc) {
-            NNS_CUDA(cudaMalloc(&h->d_blockdesc, sizeof(BlockDesc) * pl.desc.size()));
-            NNS_CUDA(cudaMemcpy(h->d_blockdesc, pl.desc.data(), sizeof(BlockDesc) * pl.desc.size(),
-                                cudaMemcpyHostToDevice));
+            NNS_CUDA(cudaMalloc(&h->d_blockdesc, dbytes + sizeof(short) * pl.tidmap.size()));
+            NNS_CUDA(cudaMemcpy(h->d_blockdesc, pl.desc.data(), dbytes, cudaMemcpyHostToDevice));
+            NNS_CUDA(cudaMemcpy(static_cast<char *>(h->d_blockdesc) + dbytes, pl.tidmap.data(),
+                                sizeof(short) * pl.tidmap.size(), cudaMemcpyHostToDevice));
         }
         a.desc = static_cast<const BlockDesc *>(h->d_blockdesc);
+        a.tidmap = reinterpret_cast<const short *>(static_cast<const char *>(h->d_blockdesc) + dbytes);
     }
     if (pl.mode == 1 && !h->d_cprime)
         NNS_CUDA(cudaMalloc(&h->d_cprime, sizeof(double) * 2 * (size_t)pl.HS * h->g.batch));
