@@ -149,6 +149,40 @@ int32_t nns_direct_fd_run(nns_handle *h, double *u, double *v, double *p, int32_
 int32_t nns_direct_fd_run_host(nns_handle *h, double *u, double *v, double *p, int32_t nsteps,
                                double *traj_u, double *traj_v, double *traj_p);
 
+/* ---- chorin_spectral (src/chorin_spectral/simulate.py) ----------------------------- */
+
+/* Number of operator arrays nns_spectral_set_operators expects, and the order:
+ *   0 Dx  1 Dy  2 Dx_sqr  3 Dy_sqr                 interiors [1:-1,1:-1] of the matrices of :84-90
+ *   4 uPinv 5 uQinv 6 uP 7 uQ  8 vPinv 9 vQinv 10 vP 11 vQ      Helmholtz eigenbases :174-183
+ *   12 u_lambda_x 13 u_lambda_y 14 v_lambda_x 15 v_lambda_y
+ *   16 pPinv 17 pQinv 18 pP 19 pQ 20 p_lambda_x 21 p_lambda_y   Uzawa operator :196-199
+ *   22 DxDPx 23 DyDPy (:193-194)   24 S (n x m, :353-361)
+ *   25 bvec_u 26 bvec_v = [b0_x(n) | bN_x(n) | b0_y(m) | bN_y(m)] (:102-118)
+ *   27 sc_u 28 sc_v = [1/e_x, x0 constant, 1/e_y, y0 constant]    (:322-334)
+ * with n = nx-2, m = ny-2; x-operators are n x n, y-operators m x m, all row-major float64. */
+#define NNS_SPECTRAL_N_OPERATORS 29
+
+/* Upload the operators of _pseudospectral_setup (chorin_spectral/simulate.py:59-199).  They are
+ * built on the HOST exactly as the reference builds them (numpy + LAPACK eig/inv, one-time)
+ * so that only the GEMM summation order differs from the reference.  ops: host pointers. */
+int32_t nns_spectral_set_operators(nns_handle *h, const double *const *ops, int32_t n_ops);
+
+/* Stage entry points (device pointers, [batch][nx][ny]):
+ *   predictor: _predictor_step :232-337   un, vn, un1, vn1 -> ui, vi
+ *   correct  : _correction_step :339-383  ui, vi, p -> u_out, v_out, p_out (p_out may alias p);
+ *              q_out: optional [batch][nx-2][ny-2] copy of the pressure Q (:370-375) or NULL */
+int32_t nns_spectral_predictor(nns_handle *h, const double *un, const double *vn, const double *un1,
+                               const double *vn1, double *ui, double *vi, void *stream);
+int32_t nns_spectral_correct(nns_handle *h, const double *ui, const double *vi, const double *p, double *u_out,
+                             double *v_out, double *p_out, double *q_out, void *stream);
+
+/* nsteps of step() with the rotation of simulate() (:547-570); same conventions as
+ * nns_chorin_fd_run / nns_chorin_fd_run_host. */
+int32_t nns_spectral_run(nns_handle *h, double *u, double *v, double *u1, double *v1, double *p, int32_t nsteps,
+                         double *traj_u, double *traj_v, double *traj_p, void *stream);
+int32_t nns_spectral_run_host(nns_handle *h, double *u, double *v, double *u1, double *v1, double *p,
+                              int32_t nsteps, double *traj_u, double *traj_v, double *traj_p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@ SOLVER_CHORIN_FD, SOLVER_DIRECT_FD, SOLVER_CHORIN_SPECTRAL = 0, 1, 2
 METHODS = {"explicit": 0, "semi_implicit": 1}
 FIELD_U, FIELD_V, FIELD_P = 0, 1, 2
 FLAG_CHECK_FINITE = 1
+SPECTRAL_N_OPERATORS = 29
 MAX_BC = 8
 
 
@@ -50,6 +51,11 @@ _PROTOS = {
     "nns_chorin_fd_correct": (_i32, [_vp] * 7),
     "nns_direct_fd_run": (_i32, [_vp] * 4 + [_i32] + [_vp] * 4),
     "nns_direct_fd_run_host": (_i32, [_vp] * 4 + [_i32] + [_vp] * 3),
+    "nns_spectral_set_operators": (_i32, [_vp, C.POINTER(_vp), _i32]),
+    "nns_spectral_predictor": (_i32, [_vp] * 8),
+    "nns_spectral_correct": (_i32, [_vp] * 9),
+    "nns_spectral_run": (_i32, [_vp] * 6 + [_i32] + [_vp] * 4),
+    "nns_spectral_run_host": (_i32, [_vp] * 6 + [_i32] + [_vp] * 3),
 }
 
 _lib = None

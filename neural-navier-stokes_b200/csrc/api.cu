@@ -25,6 +25,13 @@ int chorin_chip_run(nns_handle *h, double *bufU[3], double *bufV[3], double *p, 
                     cudaStream_t st, int m0, int count);
 bool chorin_chip_fits(const nns_handle *h);
 void chorin_chip_free_plan(nns_handle *h);
+// chorin_fd_stream.cu
+bool chorin_stream_eligible(const nns_handle *h, int phases, int nsteps);
+void chorin_stream_free(nns_handle *h);
+int chorin_stream_step(nns_handle *h, const double *uc, const double *vc, const double *up, const double *vp,
+                       double *un, double *vn, double *p, double *tu, double *tv, double *tp,
+                       size_t traj_member_stride, size_t traj_off, int32_t *sweeps, cudaStream_t st, int m0,
+                       int count);
 // chorin_fd_tiled.cu
 int chorin_tiled_run(nns_handle *h, double *bufU[3], double *bufV[3], double *p, int nsteps, int nsteps_total,
                      int step0, int phases, int fixup, double *tu, double *tv, double *tp, int32_t *sweeps,
@@ -33,6 +40,15 @@ int chorin_tiled_run(nns_handle *h, double *bufU[3], double *bufV[3], double *p,
 int direct_run(nns_handle *h, double *u, double *v, double *p, int nsteps, double *tu, double *tv, double *tp,
                cudaStream_t st);
 int launch_apply_bc(nns_handle *h, int field, double *a, cudaStream_t st);
+// spectral.cu
+int spectral_create(nns_handle *h, const double *const *mats, int n_mats);
+void spectral_destroy(nns_handle *h);
+int spectral_predictor(nns_handle *h, const double *un, const double *vn, const double *un1, const double *vn1,
+                       double *ui, double *vi, cudaStream_t st);
+int spectral_correct(nns_handle *h, const double *ui, const double *vi, const double *p, double *uo, double *vo,
+                     double *po, double *Qout, cudaStream_t st);
+int spectral_run(nns_handle *h, double *bufU[3], double *bufV[3], double *p, int nsteps, double *tu, double *tv,
+                 double *tp, cudaStream_t st);
 
 static int ensure_scratch(nns_handle *h, int k) {
     if (h->d_scratch[k]) return NNS_OK;
@@ -43,6 +59,34 @@ static int ensure_scratch(nns_handle *h, int k) {
 static int chorin_dispatch(nns_handle *h, double *bufU[3], double *bufV[3], double *p, int nsteps,
                            int nsteps_total, int step0, int phases, int fixup, double *tu, double *tv,
                            double *tp, int32_t *sweeps, cudaStream_t st, int m0 = 0, int count = -1) {
+    if (chorin_stream_eligible(h, phases, nsteps)) {
+        // persistent warp-specialised kernel: one launch per step over all members of the range
+        const size_t N = (size_t)h->g.nx * h->g.ny;
+        const int cnt = count < 0 ? h->g.batch - m0 : count;
+        const size_t bytes = sizeof(double) * N * cnt;
+        int cur = 0, prev = 1, nxt = 2, rc;
+        for (int n = 0; n < nsteps; ++n) {
+            rc = chorin_stream_step(h, bufU[cur], bufV[cur], bufU[prev], bufV[prev], bufU[nxt], bufV[nxt], p, tu, tv, tp,
+                                    (size_t)nsteps_total * N, (size_t)(step0 + n) * N,
+                                    sweeps ? sweeps + (size_t)(step0 + n) * h->g.batch : nullptr, st, m0, cnt);
+            if (rc != NNS_OK) return rc;
+            const int t = prev; prev = cur; cur = nxt; nxt = t;
+        }
+        if (fixup && cur != 0) {
+            if (cur == 2) {          // (cur, prev) = (2, 0)
+                NNS_CUDA(cudaMemcpyAsync(bufU[1], bufU[0], bytes, cudaMemcpyDeviceToDevice, st));
+                NNS_CUDA(cudaMemcpyAsync(bufV[1], bufV[0], bytes, cudaMemcpyDeviceToDevice, st));
+                NNS_CUDA(cudaMemcpyAsync(bufU[0], bufU[2], bytes, cudaMemcpyDeviceToDevice, st));
+                NNS_CUDA(cudaMemcpyAsync(bufV[0], bufV[2], bytes, cudaMemcpyDeviceToDevice, st));
+            } else {                 // (cur, prev) = (1, 2)
+                NNS_CUDA(cudaMemcpyAsync(bufU[0], bufU[1], bytes, cudaMemcpyDeviceToDevice, st));
+                NNS_CUDA(cudaMemcpyAsync(bufV[0], bufV[1], bytes, cudaMemcpyDeviceToDevice, st));
+                NNS_CUDA(cudaMemcpyAsync(bufU[1], bufU[2], bytes, cudaMemcpyDeviceToDevice, st));
+                NNS_CUDA(cudaMemcpyAsync(bufV[1], bufV[2], bytes, cudaMemcpyDeviceToDevice, st));
+            }
+        }
+        return NNS_OK;
+    }
     if (chorin_chip_fits(h))
         return chorin_chip_run(h, bufU, bufV, p, nsteps, nsteps_total, step0, phases, fixup, tu, tv, tp, sweeps, st,
                                m0, count);
@@ -144,6 +188,8 @@ int32_t nns_destroy(nns_handle *h) {
     cudaFree(h->d_nu); cudaFree(h->d_bcval); cudaFree(h->d_cprime); cudaFree(h->d_b); cudaFree(h->d_p2);
     cudaFree(h->d_sweeps); cudaFree(h->d_nonfinite); cudaFree(h->d_blockdesc);
     chorin_chip_free_plan(h);
+    chorin_stream_free(h);
+    spectral_destroy(h);
     for (int k = 0; k < 4; ++k) cudaFree(h->d_scratch[k]);
     for (int k = 0; k < 7; ++k) cudaFree(h->d_stage[k]);
     for (int k = 0; k < 4; ++k) if (h->streams[k]) cudaStreamDestroy(h->streams[k]);
@@ -365,6 +411,87 @@ int32_t nns_direct_fd_run_host(nns_handle *h, double *u, double *v, double *p, i
         int64_t c = 0;
         if (nns_nonfinite_count(h, &c) == NNS_OK && c > 0) {
             set_error("non-finite values in u/v/p (%lld cells)", (long long)c);
+            rc = NNS_ERR_NONFINITE;
+        }
+    }
+    return rc;
+}
+
+// ---- chorin_spectral --------------------------------------------------------------------------
+
+int32_t nns_spectral_set_operators(nns_handle *h, const double *const *ops, int32_t n_ops) {
+    NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_SPECTRAL);
+    if (!ops) { set_error("nns_spectral_set_operators: null argument"); return NNS_ERR_INVALID; }
+    return spectral_create(h, ops, n_ops);
+}
+
+#define NNS_CHECK_SPECTRAL(h)                                                                                   \
+    do {                                                                                                        \
+        NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_SPECTRAL);                                                        \
+        if (!(h)->spectral) { set_error("chorin_spectral: call nns_spectral_set_operators first"); return NNS_ERR_INVALID; } \
+    } while (0)
+
+int32_t nns_spectral_predictor(nns_handle *h, const double *un, const double *vn, const double *un1,
+                               const double *vn1, double *ui, double *vi, void *stream) {
+    NNS_CHECK_SPECTRAL(h);
+    if (!un || !vn || !un1 || !vn1 || !ui || !vi) { set_error("nns_spectral_predictor: null field"); return NNS_ERR_INVALID; }
+    return spectral_predictor(h, un, vn, un1, vn1, ui, vi, (cudaStream_t)stream);
+}
+
+int32_t nns_spectral_correct(nns_handle *h, const double *ui, const double *vi, const double *p, double *u_out,
+                             double *v_out, double *p_out, double *q_out, void *stream) {
+    NNS_CHECK_SPECTRAL(h);
+    if (!ui || !vi || !p || !u_out || !v_out || !p_out) { set_error("nns_spectral_correct: null field"); return NNS_ERR_INVALID; }
+    if (u_out == ui || v_out == vi) { set_error("nns_spectral_correct: u_out/v_out alias ui/vi"); return NNS_ERR_INVALID; }
+    return spectral_correct(h, ui, vi, p, u_out, v_out, p_out, q_out, (cudaStream_t)stream);
+}
+
+int32_t nns_spectral_run(nns_handle *h, double *u, double *v, double *u1, double *v1, double *p, int32_t nsteps,
+                         double *tu, double *tv, double *tp, void *stream) {
+    NNS_CHECK_SPECTRAL(h);
+    if (!u || !v || !u1 || !v1 || !p || nsteps < 0) { set_error("nns_spectral_run: bad argument"); return NNS_ERR_INVALID; }
+    if ((tu || tv || tp) && !(tu && tv && tp)) { set_error("nns_spectral_run: pass all three trajectory buffers or none"); return NNS_ERR_INVALID; }
+    if (nsteps == 0) return NNS_OK;
+    int rc;
+    if ((rc = ensure_scratch(h, 0)) || (rc = ensure_scratch(h, 1))) return rc;
+    double *bu[3] = {u, u1, h->d_scratch[0]};
+    double *bv[3] = {v, v1, h->d_scratch[1]};
+    return spectral_run(h, bu, bv, p, nsteps, tu, tv, tp, (cudaStream_t)stream);
+}
+
+int32_t nns_spectral_run_host(nns_handle *h, double *u, double *v, double *u1, double *v1, double *p,
+                              int32_t nsteps, double *tu, double *tv, double *tp) {
+    NNS_CHECK_SPECTRAL(h);
+    if (!u || !v || !u1 || !v1 || !p || nsteps < 0) { set_error("nns_spectral_run_host: bad argument"); return NNS_ERR_INVALID; }
+    const size_t bytes = sizeof(double) * (size_t)h->g.nx * h->g.ny * h->g.batch;
+    DevBuf f[5], t[3];
+    int rc;
+    double *hostf[5] = {u, v, u1, v1, p};
+    for (int k = 0; k < 5; ++k) {
+        if ((rc = f[k].alloc(bytes))) return rc;
+        NNS_CUDA(cudaMemcpy(f[k].p, hostf[k], bytes, cudaMemcpyHostToDevice));
+    }
+    double *hostt[3] = {tu, tv, tp};
+    const bool traj = tu && tv && tp && nsteps > 0;
+    if (traj)
+        for (int k = 0; k < 3; ++k)
+            if ((rc = t[k].alloc(bytes * nsteps))) return rc;
+    rc = nns_spectral_run(h, f[0].p, f[1].p, f[2].p, f[3].p, f[4].p, nsteps, traj ? t[0].p : nullptr,
+                          traj ? t[1].p : nullptr, traj ? t[2].p : nullptr, nullptr);
+    if (rc == NNS_OK) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { set_error("kernel failed: %s", cudaGetErrorString(e)); rc = NNS_ERR_CUDA; }
+    }
+    if (rc == NNS_OK) {
+        for (int k = 0; k < 5; ++k) cudaMemcpy(hostf[k], f[k].p, bytes, cudaMemcpyDeviceToHost);
+        if (traj) for (int k = 0; k < 3; ++k) cudaMemcpy(hostt[k], t[k].p, bytes * nsteps, cudaMemcpyDeviceToHost);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { set_error("copy back failed: %s", cudaGetErrorString(e)); rc = NNS_ERR_CUDA; }
+    }
+    if (rc == NNS_OK && (h->params.flags & NNS_FLAG_CHECK_FINITE)) {
+        int64_t c = 0;
+        if (nns_nonfinite_count(h, &c) == NNS_OK && c > 0) {
+            set_error("non-finite values in u/v/p (%lld cells): the reference raises here (warnings are errors, chorin_spectral:3)", (long long)c);
             rc = NNS_ERR_NONFINITE;
         }
     }

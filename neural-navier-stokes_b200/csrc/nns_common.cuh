@@ -41,6 +41,8 @@ struct nns_handle {
     void *chip_plan;          // chorin_fd chip path: cached ChipPlan (host) and block table (device)
     void *d_blockdesc;
     double *d_cprime;         // SOR right-hand side when it does not fit in shared memory
+    void *stream_plan;        // chorin_fd persistent stream path: block tables + C' images
+    void *spectral;           // chorin_spectral: SpectralPlan (operators + workspace)
     double *d_b;              // direct_fd rhs / second p buffer
     double *d_p2;
     int32_t *d_sweeps;        // [batch] scratch

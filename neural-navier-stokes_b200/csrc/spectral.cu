@@ -1,0 +1,402 @@
+// spectral.cu -- Chebyshev pseudo-spectral Chorin step (src/chorin_spectral/simulate.py of the
+// reference): every derivative / Helmholtz / Uzawa operator is a dense (N-2)x(N-2) fp64 matrix
+// product, 28 of them per step (the reference issues 32; 4 of its second-derivative products
+// are never used, :271,:274).
+//
+// The operators are built on the HOST exactly as the reference builds them (numpy loops +
+// LAPACK eig/inv, one-time, :59-199) and uploaded verbatim, so only the GEMM summation order
+// differs from the reference.  The device side is a table-driven batched fp64 GEMM kernel
+// (all products of one dependency level in ONE launch) plus a few fused pointwise kernels.
+//
+// Tensor cores: tcgen05 has no f64 kind, and on B200 the legacy DMMA path (mma.sync m8n8k4.f64)
+// has the same peak as the FP64 FMA pipe (NVIDIA quotes 40 TFLOP/s for both), so these
+// 126^3-class products run on DFMA with register tiling; see DESIGN.md.
+#include "nns_common.cuh"
+
+namespace nns {
+
+// C[b] (m x n, ldc) = op(A)[b] (m x k) * op(B)[b] (k x n), optional epilogue
+//   transB: B is stored n x k (row-major) and used as B^T
+//   epi 1 : C /= (e0 + e1 * lx[i] + e2 * ly[j])
+struct GemmDesc {
+    const double *A, *B;
+    double *C;
+    long long sA, sB, sC;     // batch strides (0 = shared operand)
+    int lda, ldb, ldc;
+    int m, n, k;
+    int transB;
+    int epi;
+    const double *lx, *ly;
+    double e0, e1, e2;
+};
+
+#define NNS_MAX_GEMM 12
+struct GemmTable {
+    GemmDesc g[NNS_MAX_GEMM];
+    int n;
+};
+
+constexpr int TM = 32, TN = 32, TK = 16;
+
+__global__ void __launch_bounds__(256) spectral_gemm_kernel(const GemmTable tab, int batch) {
+    const int gi = blockIdx.z / batch, b = blockIdx.z - gi * batch;
+    const GemmDesc &d = tab.g[gi];
+    const int row0 = blockIdx.y * TM, col0 = blockIdx.x * TN;
+    if (row0 >= d.m || col0 >= d.n) return;
+    __shared__ double As[TK][TM + 1];
+    __shared__ double Bs[TK][TN + 1];
+    const double *A = d.A + (long long)b * d.sA, *B = d.B + (long long)b * d.sB;
+    double *C = d.C + (long long)b * d.sC;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16 threads, 2 x 2 outputs each
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    for (int k0 = 0; k0 < d.k; k0 += TK) {
+        for (int q = threadIdx.x; q < TM * TK; q += 256) {
+            const int r = q / TK, kk = q - r * TK;               // A tile: rows row0.., cols k0..
+            const int gr = row0 + r, gk = k0 + kk;
+            As[kk][r] = (gr < d.m && gk < d.k) ? A[(long long)gr * d.lda + gk] : 0.0;
+        }
+        if (d.transB) {
+            for (int q = threadIdx.x; q < TN * TK; q += 256) {
+                const int c = q / TK, kk = q - c * TK;           // B stored n x k
+                const int gc = col0 + c, gk = k0 + kk;
+                Bs[kk][c] = (gc < d.n && gk < d.k) ? B[(long long)gc * d.ldb + gk] : 0.0;
+            }
+        } else {
+            for (int q = threadIdx.x; q < TN * TK; q += 256) {
+                const int kk = q / TN, c = q - kk * TN;          // B stored k x n
+                const int gc = col0 + c, gk = k0 + kk;
+                Bs[kk][c] = (gc < d.n && gk < d.k) ? B[(long long)gk * d.ldb + gc] : 0.0;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < TK; ++kk) {
+            const double a0 = As[kk][ty], a1 = As[kk][ty + 16];
+            const double b0 = Bs[kk][tx], b1 = Bs[kk][tx + 16];
+            acc[0][0] = fma(a0, b0, acc[0][0]);
+            acc[0][1] = fma(a0, b1, acc[0][1]);
+            acc[1][0] = fma(a1, b0, acc[1][0]);
+            acc[1][1] = fma(a1, b1, acc[1][1]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int gr = row0 + ty + 16 * r, gc = col0 + tx + 16 * c;
+            if (gr < d.m && gc < d.n) {
+                double v = acc[r][c];
+                if (d.epi == 1) v = v / (d.e0 + d.e1 * d.lx[gr] + d.e2 * d.ly[gc]);
+                C[(long long)gr * d.ldc + gc] = v;
+            }
+        }
+}
+
+// F = 2 f - 3dt (u f_x + v f_y) + dt (u1 f1_x + v1 f1_y) + dt (f_xx + f_yy)   (chorin_spectral:277-282)
+__global__ void spectral_rhs_kernel(const double *__restrict__ un, const double *__restrict__ vn,
+                                    const double *__restrict__ un1, const double *__restrict__ vn1,
+                                    const double *__restrict__ W, double *__restrict__ Fu, double *__restrict__ Fv,
+                                    int nx, int ny, double dt, long long wstride) {
+    const int n = nx - 2, m = ny - 2;
+    const long long b = blockIdx.y;
+    const size_t N = (size_t)nx * ny, NI = (size_t)n * m;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < NI; q += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(q / m), j = (int)(q - (size_t)i * m);
+        const size_t g = b * N + (size_t)(i + 1) * ny + (j + 1);
+        const double u = un[g], v = vn[g], u1 = un1[g], v1 = vn1[g];
+        const double *w = W + b * NI + q;       // 12 derivative planes, plane stride wstride
+        const double un_dx = w[0], un_dy = w[wstride], un1_dx = w[2 * wstride], un1_dy = w[3 * wstride];
+        const double vn_dx = w[4 * wstride], vn_dy = w[5 * wstride], vn1_dx = w[6 * wstride], vn1_dy = w[7 * wstride];
+        const double un_ddx = w[8 * wstride], un_ddy = w[9 * wstride], vn_ddx = w[10 * wstride], vn_ddy = w[11 * wstride];
+        Fu[b * NI + q] = 2.0 * u - 3.0 * dt * (u * un_dx + v * un_dy) + dt * (u1 * un1_dx + v1 * un1_dy) +
+                         dt * (un_ddx + un_ddy);
+        Fv[b * NI + q] = 2.0 * v - 3.0 * dt * (u * vn_dx + v * vn_dy) + dt * (u1 * vn1_dx + v1 * vn1_dy) +
+                         dt * (vn_ddx + vn_ddy);
+    }
+}
+
+// Boundary rows / columns of the predictor from the interior solution (chorin_spectral:249-254,
+// 322-334), corners zero.  bvec = [b0_x(n) | bN_x(n) | b0_y(m) | bN_y(m)], sc = [1/e_x, const_x0, 1/e_y, const_y0].
+__global__ void spectral_boundary_kernel(double *__restrict__ A, const double *__restrict__ bvec,
+                                         const double *__restrict__ sc, int nx, int ny) {
+    const int n = nx - 2, m = ny - 2;
+    double *F = A + (size_t)blockIdx.y * nx * ny;
+    const double *b0x = bvec, *bNx = bvec + n, *b0y = bvec + 2 * n, *bNy = bvec + 2 * n + m;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < m) {                 // x0 / xN rows: reduce over i for column j = t
+        double s0 = 0.0, sN = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double v = F[(size_t)(i + 1) * ny + t + 1];
+            s0 += b0x[i] * v;
+            sN += bNx[i] * v;
+        }
+        F[t + 1] = sc[0] * s0 + sc[1];
+        F[(size_t)(nx - 1) * ny + t + 1] = sc[0] * sN;
+    } else if (t < m + n) {      // y0 / yN columns: reduce over j for row i
+        const int i = t - m;
+        double s0 = 0.0, sN = 0.0;
+        for (int j = 0; j < m; ++j) {
+            const double v = F[(size_t)(i + 1) * ny + j + 1];
+            s0 += b0y[j] * v;
+            sN += bNy[j] * v;
+        }
+        F[(size_t)(i + 1) * ny] = sc[2] * s0 + sc[3];
+        F[(size_t)(i + 1) * ny + ny - 1] = sc[2] * sN;
+    } else if (t == m + n) {
+        F[0] = 0.0; F[ny - 1] = 0.0; F[(size_t)(nx - 1) * ny] = 0.0; F[(size_t)(nx - 1) * ny + ny - 1] = 0.0;
+    }
+}
+
+// H = -rho/dt (S - G1 - G2)   (chorin_spectral:367)
+__global__ void spectral_uzawa_rhs_kernel(const double *__restrict__ S, const double *__restrict__ G1,
+                                          const double *__restrict__ G2, double *__restrict__ H, size_t NI,
+                                          double rho_dt) {
+    const size_t b = blockIdx.y;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < NI; q += (size_t)gridDim.x * blockDim.x)
+        H[b * NI + q] = -rho_dt * (S[q] - G1[b * NI + q] - G2[b * NI + q]);
+}
+
+// u = ui - (DxDPx Q) dt/rho, v = vi - (Q DyDPy^T) dt/rho, p[interior] = Q, edges copied
+// (chorin_spectral:378-381)
+__global__ void spectral_project_kernel(const double *__restrict__ ui, const double *__restrict__ vi,
+                                        const double *p, const double *__restrict__ G3,
+                                        const double *__restrict__ G4, const double *__restrict__ Q,
+                                        double *__restrict__ uo, double *__restrict__ vo, double *po,
+                                        int nx, int ny, double dt, double rho) {
+    const int n = nx - 2, m = ny - 2;
+    const size_t b = blockIdx.y, N = (size_t)nx * ny, NI = (size_t)n * m;
+    (void)n;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(q / ny), j = (int)(q - (size_t)i * ny);
+        double u = ui[b * N + q], v = vi[b * N + q], pp = p[b * N + q];
+        if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1) {
+            const size_t qi = b * NI + (size_t)(i - 1) * m + (j - 1);
+            u = u - G3[qi] * dt / rho;
+            v = v - G4[qi] * dt / rho;
+            pp = Q[qi];
+        }
+        uo[b * N + q] = u;
+        vo[b * N + q] = v;
+        po[b * N + q] = pp;
+    }
+}
+
+// trajectory snapshot (chorin_spectral:560-562) + optional non-finite count
+__global__ void spectral_snapshot_kernel(const double *__restrict__ u, const double *__restrict__ v,
+                                         const double *__restrict__ p, double *tu, double *tv, double *tp, size_t N,
+                                         int nsteps_total, int step, unsigned long long *nonfinite, int flags) {
+    const size_t b = blockIdx.y;
+    const size_t toff = (b * nsteps_total + step) * N;
+    unsigned long long bad = 0;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += (size_t)gridDim.x * blockDim.x) {
+        const double x = u[b * N + q], y = v[b * N + q], z = p[b * N + q];
+        if (tu) { tu[toff + q] = x; tv[toff + q] = y; tp[toff + q] = z; }
+        bad += !(isfinite(x) && isfinite(y) && isfinite(z));
+    }
+    if ((flags & NNS_FLAG_CHECK_FINITE) && bad) atomicAdd(nonfinite, bad);
+}
+
+struct SpectralPlan {
+    int nx, ny, n, m, batch;
+    double dt, rho;
+    double *mats[40];
+    double *W;        // 12 derivative planes + scratch, each batch*n*m
+    double *scratch[8];
+    double *ui, *vi;  // predictor outputs of the run loop
+};
+
+static int run_table(nns_handle *h, GemmTable &t, int batch, cudaStream_t st) {
+    int mm = 0, nn = 0;
+    for (int i = 0; i < t.n; ++i) { mm = t.g[i].m > mm ? t.g[i].m : mm; nn = t.g[i].n > nn ? t.g[i].n : nn; }
+    dim3 grid((nn + TN - 1) / TN, (mm + TM - 1) / TM, t.n * batch);
+    spectral_gemm_kernel<<<grid, 256, 0, st>>>(t, batch);
+    NNS_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return NNS_OK;
+}
+
+static GemmDesc mk(const double *A, int lda, long long sA, const double *B, int ldb, long long sB, int transB,
+                   double *C, int ldc, long long sC, int m, int n, int k) {
+    GemmDesc d{};
+    d.A = A; d.B = B; d.C = C; d.sA = sA; d.sB = sB; d.sC = sC; d.lda = lda; d.ldb = ldb; d.ldc = ldc;
+    d.m = m; d.n = n; d.k = k; d.transB = transB; d.epi = 0;
+    return d;
+}
+
+enum {  // indices into SpectralPlan::mats == the order of the pointers passed to nns_spectral_create
+    M_DX = 0, M_DY, M_DX2, M_DY2, M_UPINV, M_UQINV, M_UP, M_UQ, M_VPINV, M_VQINV, M_VP, M_VQ,
+    M_ULX, M_ULY, M_VLX, M_VLY, M_PPINV, M_PQINV, M_PP, M_PQ, M_PLX, M_PLY, M_DXDPX, M_DYDPY, M_S,
+    M_BVEC_U, M_BVEC_V, M_SC_U, M_SC_V, M_COUNT
+};
+
+void spectral_destroy(nns_handle *h);
+
+int spectral_create(nns_handle *h, const double *const *mats, int n_mats) {
+    spectral_destroy(h);
+    if (n_mats != M_COUNT) { set_error("nns_spectral_create: expected %d operator arrays, got %d", (int)M_COUNT, n_mats); return NNS_ERR_INVALID; }
+    SpectralPlan *sp = new SpectralPlan();
+    memset(sp, 0, sizeof(*sp));
+    sp->nx = h->g.nx; sp->ny = h->g.ny; sp->n = h->g.nx - 2; sp->m = h->g.ny - 2; sp->batch = h->g.batch;
+    sp->dt = h->g.dt; sp->rho = h->g.rho;
+    const int n = sp->n, m = sp->m;
+    const size_t sizes[M_COUNT] = {
+        (size_t)n * n, (size_t)m * m, (size_t)n * n, (size_t)m * m,
+        (size_t)n * n, (size_t)m * m, (size_t)n * n, (size_t)m * m, (size_t)n * n, (size_t)m * m, (size_t)n * n, (size_t)m * m,
+        (size_t)n, (size_t)m, (size_t)n, (size_t)m,
+        (size_t)n * n, (size_t)m * m, (size_t)n * n, (size_t)m * m, (size_t)n, (size_t)m,
+        (size_t)n * n, (size_t)m * m, (size_t)n * m,
+        (size_t)2 * n + 2 * m, (size_t)2 * n + 2 * m, 4, 4};
+    h->spectral = sp;
+    for (int i = 0; i < M_COUNT; ++i) {
+        if (!mats[i]) { set_error("nns_spectral_create: operator %d is null", i); return NNS_ERR_INVALID; }
+        NNS_CUDA(cudaMalloc(&sp->mats[i], sizeof(double) * sizes[i]));
+        NNS_CUDA(cudaMemcpy(sp->mats[i], mats[i], sizeof(double) * sizes[i], cudaMemcpyHostToDevice));
+    }
+    const size_t NI = (size_t)n * m * sp->batch;
+    NNS_CUDA(cudaMalloc(&sp->W, sizeof(double) * NI * 12));
+    for (int i = 0; i < 8; ++i) NNS_CUDA(cudaMalloc(&sp->scratch[i], sizeof(double) * NI));
+    return NNS_OK;
+}
+
+void spectral_destroy(nns_handle *h) {
+    SpectralPlan *sp = static_cast<SpectralPlan *>(h->spectral);
+    if (!sp) return;
+    for (int i = 0; i < 40; ++i) cudaFree(sp->mats[i]);
+    cudaFree(sp->W);
+    for (int i = 0; i < 8; ++i) cudaFree(sp->scratch[i]);
+    cudaFree(sp->ui); cudaFree(sp->vi);
+    delete sp;
+    h->spectral = nullptr;
+}
+
+// _predictor_step (chorin_spectral:232-337): un,vn,un1,vn1 -> ui, vi   (all [batch][nx][ny])
+int spectral_predictor(nns_handle *h, const double *un, const double *vn, const double *un1, const double *vn1,
+                       double *ui, double *vi, cudaStream_t st) {
+    SpectralPlan *sp = static_cast<SpectralPlan *>(h->spectral);
+    const int nx = sp->nx, ny = sp->ny, n = sp->n, m = sp->m, B = sp->batch;
+    const long long N = (long long)nx * ny, NI = (long long)n * m, WS = NI * B;
+    const int off = ny + 1;                     // interior view of a [nx][ny] field
+    double **M = sp->mats;
+    int rc;
+    GemmTable t{};
+    const double *f[4] = {un, un1, vn, vn1};
+    for (int q = 0; q < 4; ++q) {               // planes 0..7: Dx f, f Dy^T for f = un, un1, vn, vn1
+        t.g[t.n++] = mk(M[M_DX], n, 0, f[q] + off, ny, N, 0, sp->W + (2 * q) * WS, m, NI, n, m, n);
+        t.g[t.n++] = mk(f[q] + off, ny, N, M[M_DY], m, 0, 1, sp->W + (2 * q + 1) * WS, m, NI, n, m, m);
+    }
+    t.g[t.n++] = mk(M[M_DX2], n, 0, un + off, ny, N, 0, sp->W + 8 * WS, m, NI, n, m, n);
+    t.g[t.n++] = mk(un + off, ny, N, M[M_DY2], m, 0, 1, sp->W + 9 * WS, m, NI, n, m, m);
+    t.g[t.n++] = mk(M[M_DX2], n, 0, vn + off, ny, N, 0, sp->W + 10 * WS, m, NI, n, m, n);
+    t.g[t.n++] = mk(vn + off, ny, N, M[M_DY2], m, 0, 1, sp->W + 11 * WS, m, NI, n, m, m);
+    if ((rc = run_table(h, t, B, st))) return rc;
+    double *Fu = sp->scratch[0], *Fv = sp->scratch[1], *T0 = sp->scratch[2], *T1 = sp->scratch[3];
+    spectral_rhs_kernel<<<dim3(64, B), 256, 0, st>>>(un, vn, un1, vn1, sp->W, Fu, Fv, nx, ny, sp->dt, WS);
+    h->launches += 1;
+    // Helmholtz solves by diagonalisation (:285-298), u and v side by side in every launch
+    t = GemmTable{};
+    t.g[t.n++] = mk(M[M_UPINV], n, 0, Fu, m, NI, 0, T0, m, NI, n, m, n);
+    t.g[t.n++] = mk(M[M_VPINV], n, 0, Fv, m, NI, 0, T1, m, NI, n, m, n);
+    if ((rc = run_table(h, t, B, st))) return rc;
+    t = GemmTable{};
+    t.g[t.n++] = mk(T0, m, NI, M[M_UQINV], m, 0, 1, Fu, m, NI, n, m, m);
+    t.g[t.n++] = mk(T1, m, NI, M[M_VQINV], m, 0, 1, Fv, m, NI, n, m, m);
+    t.g[0].epi = 1; t.g[0].lx = M[M_ULX]; t.g[0].ly = M[M_ULY]; t.g[0].e0 = 2.0; t.g[0].e1 = -sp->dt; t.g[0].e2 = -sp->dt;
+    t.g[1].epi = 1; t.g[1].lx = M[M_VLX]; t.g[1].ly = M[M_VLY]; t.g[1].e0 = 2.0; t.g[1].e1 = -sp->dt; t.g[1].e2 = -sp->dt;
+    if ((rc = run_table(h, t, B, st))) return rc;
+    t = GemmTable{};
+    t.g[t.n++] = mk(Fu, m, NI, M[M_UQ], m, 0, 1, T0, m, NI, n, m, m);
+    t.g[t.n++] = mk(Fv, m, NI, M[M_VQ], m, 0, 1, T1, m, NI, n, m, m);
+    if ((rc = run_table(h, t, B, st))) return rc;
+    t = GemmTable{};                            // solution straight into the interiors of ui, vi
+    t.g[t.n++] = mk(M[M_UP], n, 0, T0, m, NI, 0, ui + off, ny, N, n, m, n);
+    t.g[t.n++] = mk(M[M_VP], n, 0, T1, m, NI, 0, vi + off, ny, N, n, m, n);
+    if ((rc = run_table(h, t, B, st))) return rc;
+    const int tb = (n + m + 1 + 127) / 128;
+    spectral_boundary_kernel<<<dim3(tb, B), 128, 0, st>>>(ui, M[M_BVEC_U], M[M_SC_U], nx, ny);
+    spectral_boundary_kernel<<<dim3(tb, B), 128, 0, st>>>(vi, M[M_BVEC_V], M[M_SC_V], nx, ny);
+    h->launches += 2;
+    NNS_CUDA(cudaGetLastError());
+    return NNS_OK;
+}
+
+// _correction_step (chorin_spectral:339-383): ui, vi, p -> u, v, p_out (+ optional Q [batch][n][m])
+int spectral_correct(nns_handle *h, const double *ui, const double *vi, const double *p, double *uo, double *vo,
+                     double *po, double *Qout, cudaStream_t st) {
+    SpectralPlan *sp = static_cast<SpectralPlan *>(h->spectral);
+    const int nx = sp->nx, ny = sp->ny, n = sp->n, m = sp->m, B = sp->batch;
+    const long long N = (long long)nx * ny, NI = (long long)n * m;
+    const int off = ny + 1;
+    double **M = sp->mats;
+    double *G1 = sp->scratch[0], *G2 = sp->scratch[1], *Hh = sp->scratch[2], *T0 = sp->scratch[3];
+    double *Q = Qout ? Qout : sp->scratch[4], *G3 = sp->scratch[5], *G4 = sp->scratch[6];
+    int rc;
+    GemmTable t{};
+    t.g[t.n++] = mk(M[M_DX], n, 0, ui + off, ny, N, 0, G1, m, NI, n, m, n);
+    t.g[t.n++] = mk(vi + off, ny, N, M[M_DY], m, 0, 1, G2, m, NI, n, m, m);
+    if ((rc = run_table(h, t, B, st))) return rc;
+    spectral_uzawa_rhs_kernel<<<dim3(64, B), 256, 0, st>>>(M[M_S], G1, G2, Hh, (size_t)NI, sp->rho / sp->dt);
+    h->launches += 1;
+    t = GemmTable{};
+    t.g[t.n++] = mk(M[M_PPINV], n, 0, Hh, m, NI, 0, T0, m, NI, n, m, n);
+    if ((rc = run_table(h, t, B, st))) return rc;
+    t = GemmTable{};
+    t.g[t.n++] = mk(T0, m, NI, M[M_PQINV], m, 0, 1, Hh, m, NI, n, m, m);
+    t.g[0].epi = 1; t.g[0].lx = M[M_PLX]; t.g[0].ly = M[M_PLY]; t.g[0].e0 = 0.0; t.g[0].e1 = 1.0; t.g[0].e2 = 1.0;
+    if ((rc = run_table(h, t, B, st))) return rc;
+    t = GemmTable{};
+    t.g[t.n++] = mk(Hh, m, NI, M[M_PQ], m, 0, 1, T0, m, NI, n, m, m);
+    if ((rc = run_table(h, t, B, st))) return rc;
+    t = GemmTable{};
+    t.g[t.n++] = mk(M[M_PP], n, 0, T0, m, NI, 0, Q, m, NI, n, m, n);
+    if ((rc = run_table(h, t, B, st))) return rc;
+    t = GemmTable{};
+    t.g[t.n++] = mk(M[M_DXDPX], n, 0, Q, m, NI, 0, G3, m, NI, n, m, n);
+    t.g[t.n++] = mk(Q, m, NI, M[M_DYDPY], m, 0, 1, G4, m, NI, n, m, m);
+    if ((rc = run_table(h, t, B, st))) return rc;
+    spectral_project_kernel<<<dim3(64, B), 256, 0, st>>>(ui, vi, p, G3, G4, Q, uo, vo, po, nx, ny, sp->dt, sp->rho);
+    h->launches += 1;
+    NNS_CUDA(cudaGetLastError());
+    return NNS_OK;
+}
+
+// nsteps of NavierStokesSystem.step + the rotation of simulate (chorin_spectral:54-57, :547-570).
+// bufU/bufV: roles at entry 0 = cur, 1 = prev, 2 = scratch; on return buffer 0 holds step n and
+// buffer 1 step n-1.
+int spectral_run(nns_handle *h, double *bufU[3], double *bufV[3], double *p, int nsteps, double *tu, double *tv,
+                 double *tp, cudaStream_t st) {
+    SpectralPlan *sp = static_cast<SpectralPlan *>(h->spectral);
+    if (!sp) { set_error("chorin_spectral: operators not uploaded (call nns_spectral_set_operators first)"); return NNS_ERR_INVALID; }
+    const size_t N = (size_t)sp->nx * sp->ny, bytes = sizeof(double) * N * sp->batch;
+    if (!sp->ui) NNS_CUDA(cudaMalloc(&sp->ui, bytes));
+    if (!sp->vi) NNS_CUDA(cudaMalloc(&sp->vi, bytes));
+    int cur = 0, prev = 1, nxt = 2, rc;
+    for (int n = 0; n < nsteps; ++n) {
+        if ((rc = spectral_predictor(h, bufU[cur], bufV[cur], bufU[prev], bufV[prev], sp->ui, sp->vi, st))) return rc;
+        if ((rc = spectral_correct(h, sp->ui, sp->vi, p, bufU[nxt], bufV[nxt], p, nullptr, st))) return rc;
+        if (tu || (h->params.flags & NNS_FLAG_CHECK_FINITE)) {
+            spectral_snapshot_kernel<<<dim3(64, sp->batch), 256, 0, st>>>(bufU[nxt], bufV[nxt], p, tu, tv, tp, N, nsteps, n,
+                                                                           h->d_nonfinite, h->params.flags);
+            h->launches += 1;
+        }
+        const int t = prev; prev = cur; cur = nxt; nxt = t;
+    }
+    NNS_CUDA(cudaGetLastError());
+    if (cur != 0) {
+        // final roles -> caller's buffers (buffer 0 = step n, buffer 1 = step n-1)
+        if (cur == 2) {          // (cur, prev) = (2, 0)
+            NNS_CUDA(cudaMemcpyAsync(bufU[1], bufU[0], bytes, cudaMemcpyDeviceToDevice, st));
+            NNS_CUDA(cudaMemcpyAsync(bufV[1], bufV[0], bytes, cudaMemcpyDeviceToDevice, st));
+            NNS_CUDA(cudaMemcpyAsync(bufU[0], bufU[2], bytes, cudaMemcpyDeviceToDevice, st));
+            NNS_CUDA(cudaMemcpyAsync(bufV[0], bufV[2], bytes, cudaMemcpyDeviceToDevice, st));
+        } else {                 // (cur, prev) = (1, 2)
+            NNS_CUDA(cudaMemcpyAsync(bufU[0], bufU[1], bytes, cudaMemcpyDeviceToDevice, st));
+            NNS_CUDA(cudaMemcpyAsync(bufV[0], bufV[1], bytes, cudaMemcpyDeviceToDevice, st));
+            NNS_CUDA(cudaMemcpyAsync(bufU[1], bufU[2], bytes, cudaMemcpyDeviceToDevice, st));
+            NNS_CUDA(cudaMemcpyAsync(bufV[1], bufV[2], bytes, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    return NNS_OK;
+}
+
+}  // namespace nns

@@ -1,0 +1,137 @@
+"""GPU parity of the persistent warp-specialised chorin_fd kernel (chorin_fd_stream.cu, the path
+BASELINE config 4 runs on: 128x128 members) against the oracle and against the one-CTA-per-member
+kernel.  Tolerance: fp64 relative L2 <= 1e-10 on u, v, p; sweep counts exact."""
+import numpy as np
+import pytest
+
+from tests._util import rel_l2, smooth_ic
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+NX = NY = 128
+
+
+def _bc_tuples(bcs):
+    return [(b.boundary, b.type, float(b.value)) for b in bcs]
+
+
+def _ens(B, u_bc, v_bc, p_bc, nu, lid=None, **kw):
+    from nns_b200.ensemble import ChorinEnsemble, cavity_bc_values
+    args = dict(u_bc=u_bc, v_bc=v_bc, p_bc=p_bc, nit=50, dt=2e-4, rho=1, nu=nu, beta=1.25, method='explicit')
+    args.update(kw)
+    if lid is not None:
+        args["bc_values"] = cavity_bc_values(lid)
+    return ChorinEnsemble(B, NX, NY, **args)
+
+
+def test_stream_many_members_vs_oracle(oracle_fd, monkeypatch):
+    """More members than SMs (several members per persistent CTA, ragged tail), cavity draw of
+    config 4, 3 steps: sampled members vs the oracle."""
+    monkeypatch.delenv("NNS_CHIP_MODE", raising=False)
+    from nns_b200.ensemble import cavity_bcs, cavity_ensemble_params
+    B = 333
+    lid, nu = cavity_ensemble_params(B, seed=5)
+    dx = dy = 2. / (NX - 1)
+    u_bc, v_bc, p_bc = cavity_bcs(dx, dy)
+    ens = _ens(B, u_bc, v_bc, p_bc, nu, lid)
+    ens.init_variables()
+    nsteps = 3
+    sw = []
+    for _ in range(nsteps):
+        ens.step()
+        sw.append(ens.sweeps.cpu().numpy().copy())
+    z = np.zeros((NX, NY))
+    for b in (0, 1, 147, 148, 149, 295, 296, 332):
+        ub = _bc_tuples(u_bc)
+        ub[1] = ("right", "dirichlet", float(lid[b]))
+        ou, ov, op, osw = oracle_fd.chorin_simulate(z, z, z, ub, _bc_tuples(v_bc), _bc_tuples(p_bc), nt=nsteps, nit=50,
+                                                    dt=2e-4, rho=1, nu=float(nu[b]), beta=1.25)
+        assert rel_l2(ens.u[b].cpu().numpy(), ou[-1]) <= TOL
+        assert rel_l2(ens.v[b].cpu().numpy(), ov[-1]) <= TOL
+        assert rel_l2(ens.p[b].cpu().numpy(), op[-1]) <= TOL
+        assert [int(s[b]) for s in sw] == list(osw)
+
+
+def test_stream_mixed_bcs_smooth_ic_vs_oracle(oracle_fd, monkeypatch):
+    """Neumann / Dirichlet mixes in list order (corners, Neumann reading freshly written lines) on
+    u, v and p with a smooth non-zero start, via run() with trajectory."""
+    monkeypatch.delenv("NNS_CHIP_MODE", raising=False)
+    import nns_b200
+    D, Nm = nns_b200.DirichletBoundaryCondition, nns_b200.NeumannBoundaryCondition
+    dx = dy = 2. / (NX - 1)
+    u_bc = [Nm(0.3, 'left', dx, dy), D(0.7, 'right', dx, dy), Nm(-0.2, 'top', dx, dy), D(0.1, 'bottom', dx, dy)]
+    v_bc = [D(0.0, 'top', dx, dy), Nm(0.5, 'bottom', dx, dy), D(-0.1, 'left', dx, dy), Nm(0.0, 'right', dx, dy)]
+    p_bc = [Nm(0.0, 'left', dx, dy), D(0.2, 'top', dx, dy), Nm(0.1, 'right', dx, dy), Nm(0.0, 'bottom', dx, dy)]
+    B = 5
+    ics = [smooth_ic(NX, NY, 40 + b) for b in range(B)]
+    ens = _ens(B, u_bc, v_bc, p_bc, 0.05, nit=30, dt=1e-4)
+    ens.set_state(np.stack([c[0] for c in ics]), np.stack([c[1] for c in ics]), np.stack([c[2] for c in ics]))
+    ens.init_variables()
+    nsteps = 4
+    tu, tv, tp, sw = ens.run(nsteps, trajectory=True, sweeps=True)
+    for b in range(B):
+        ou, ov, op, osw = oracle_fd.chorin_simulate(ics[b][0], ics[b][1], ics[b][2], _bc_tuples(u_bc), _bc_tuples(v_bc),
+                                                    _bc_tuples(p_bc), nt=nsteps, nit=30, dt=1e-4, rho=1, nu=0.05, beta=1.25)
+        for n in range(nsteps):
+            assert rel_l2(tu[b, n].cpu().numpy(), ou[n]) <= TOL
+            assert rel_l2(tv[b, n].cpu().numpy(), ov[n]) <= TOL
+            assert rel_l2(tp[b, n].cpu().numpy(), op[n]) <= TOL
+        assert list(sw[:, b].cpu().numpy()) == list(osw)
+
+
+def test_stream_early_exit_vs_oracle(oracle_fd, monkeypatch):
+    """Tiny lid velocities: the SOR loop of the reference exits after a few sweeps (different per
+    member and step); the wavefront must reproduce the exact count and the capped result."""
+    monkeypatch.delenv("NNS_CHIP_MODE", raising=False)
+    from nns_b200.ensemble import cavity_bcs
+    dx = dy = 2. / (NX - 1)
+    u_bc, v_bc, p_bc = cavity_bcs(dx, dy)
+    lid = np.array([3e-7, 1e-6, 2e-6, 1e-5, 1e-4, 1.0])
+    nu = np.full(len(lid), 0.1)
+    ens = _ens(len(lid), u_bc, v_bc, p_bc, nu, lid)
+    ens.init_variables()
+    nsteps = 3
+    sws = []
+    for _ in range(nsteps):
+        ens.step()
+        sws.append(ens.sweeps.cpu().numpy().copy())
+    sws = np.stack(sws)
+    z = np.zeros((NX, NY))
+    seen = set()
+    for b in range(len(lid)):
+        ub = _bc_tuples(u_bc)
+        ub[1] = ("right", "dirichlet", float(lid[b]))
+        ou, ov, op, osw = oracle_fd.chorin_simulate(z, z, z, ub, _bc_tuples(v_bc), _bc_tuples(p_bc), nt=nsteps, nit=50,
+                                                    dt=2e-4, rho=1, nu=0.1, beta=1.25)
+        assert list(sws[:, b]) == list(osw), (b, sws[:, b], osw)
+        seen.update(int(s) for s in osw)
+        assert rel_l2(ens.u[b].cpu().numpy(), ou[-1]) <= TOL
+        assert rel_l2(ens.p[b].cpu().numpy(), op[-1]) <= TOL
+    assert min(seen) < 49 and max(seen) == 49, seen      # the case really exercises both branches
+
+
+def test_stream_equals_member_kernel(monkeypatch):
+    """Persistent kernel vs the one-CTA-per-member register-block kernel: same arithmetic per cell,
+    so the fields agree to rounding (<= 1e-13) and the sweep counts exactly -- including with a
+    loose tolerance that makes members stop early at different sweeps."""
+    import torch
+    from nns_b200.ensemble import cavity_bcs, cavity_ensemble_params
+    B = 160
+    lid, nu = cavity_ensemble_params(B, seed=9)
+    dx = dy = 2. / (NX - 1)
+    u_bc, v_bc, p_bc = cavity_bcs(dx, dy)
+    out = {}
+    for mode in ("stream", "reg76"):
+        monkeypatch.setenv("NNS_CHIP_MODE", mode)
+        ens = _ens(B, u_bc, v_bc, p_bc, nu, lid, tol=2e-2)
+        ens.init_variables()
+        sw = []
+        for _ in range(4):
+            ens.step()
+            sw.append(ens.sweeps.clone())
+        out[mode] = (ens.u.clone(), ens.v.clone(), ens.p.clone(), torch.stack(sw))
+    a, b = out["stream"], out["reg76"]
+    assert torch.equal(a[3], b[3])
+    assert int(a[3].min()) < 49
+    for x, y in zip(a[:3], b[:3]):
+        assert float((x - y).norm() / y.norm()) <= 1e-13
