@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnns_b200.so")
+LIB_PATH = os.environ.get("NNS_B200_LIB") or os.path.join(_HERE, "libnns_b200.so")   # override: experiments only
 
 SOLVER_CHORIN_FD, SOLVER_DIRECT_FD, SOLVER_CHORIN_SPECTRAL = 0, 1, 2
 METHODS = {"explicit": 0, "semi_implicit": 1}

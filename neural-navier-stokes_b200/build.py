@@ -10,7 +10,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libnns_b200.so")
+LIB = os.environ.get("NNS_B200_LIB") or os.path.join(HERE, "libnns_b200.so")   # override: experiments only
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--cudart", "static"]
@@ -39,7 +39,8 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("NNS_EXTRA_NVCC_FLAGS", "").split() + \
+        (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
     env = dict(os.environ)
     # the image exports CC/CXX pointing at a gcc wrapper without libstdc++ specs for nvcc's host pass
     r = subprocess.run(cmd + ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else cmd,

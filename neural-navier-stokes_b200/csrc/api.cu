@@ -28,6 +28,7 @@ void chorin_chip_free_plan(nns_handle *h);
 // chorin_fd_stream.cu
 bool chorin_stream_eligible(const nns_handle *h, int phases, int nsteps);
 void chorin_stream_free(nns_handle *h);
+void chorin_stream_prof_dump(nns_handle *h);
 int chorin_stream_step(nns_handle *h, const double *uc, const double *vc, const double *up, const double *vp,
                        double *un, double *vn, double *p, double *tu, double *tv, double *tp,
                        size_t traj_member_stride, size_t traj_off, int32_t *sweeps, cudaStream_t st, int m0,
@@ -185,6 +186,7 @@ int32_t nns_create(const nns_params *P, const nns_bc *bcs, int32_t n_bcs, const 
 int32_t nns_destroy(nns_handle *h) {
     if (!h) return NNS_OK;
     cudaSetDevice(h->device);
+    chorin_stream_prof_dump(h);
     cudaFree(h->d_nu); cudaFree(h->d_bcval); cudaFree(h->d_cprime); cudaFree(h->d_b); cudaFree(h->d_p2);
     cudaFree(h->d_sweeps); cudaFree(h->d_nonfinite); cudaFree(h->d_blockdesc);
     chorin_chip_free_plan(h);

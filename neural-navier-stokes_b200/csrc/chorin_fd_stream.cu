@@ -21,15 +21,17 @@
 #include <vector>
 
 #include "nns_common.cuh"
+#include "sor_block.cuh"
 
 namespace nns {
 
 namespace {
 
-constexpr int NT_SOR = 256;     // threads of the SOR role (2 warpgroups)
 constexpr int NT_ST = 128;      // threads of the stencil role (1 warpgroup)
-constexpr int RING = 6;         // rows in flight per field in the stencil ring
-constexpr int REGS_SOR = 208, REGS_ST = 88;
+constexpr int GR = 4;           // rows per ring group (one bulk copy per field, one full/empty mbarrier pair)
+constexpr int NG = 2;           // groups in the ring (double buffer)
+constexpr int RING = GR * NG;   // rows per field in the stencil ring
+constexpr int REGS_SOR = 200, REGS_ST = 104;
 
 // named barrier ids (0 is __syncthreads)
 enum { BAR_SOR = 1, BAR_ST = 2, BAR_READY = 3, BAR_CONSUMED = 5, BAR_DONE = 7 };   // +0/+1 by member parity
@@ -37,7 +39,7 @@ enum { BAR_SOR = 1, BAR_ST = 2, BAR_READY = 3, BAR_CONSUMED = 5, BAR_DONE = 7 };
 struct SBlock {          // one per SOR thread (host-built)
     short r0, c0;        // first interior row / column of the block
     short nN, nS, nW, nE;   // thread ids of the neighbouring blocks, -1 = physical boundary
-    short bd;            // block anti-diagonal
+    short bd;            // anti-diagonal of the top sub-block: 2 * bi + bj
     short pad;
 };
 
@@ -59,11 +61,12 @@ struct StreamArgs {
     size_t traj_member_stride, traj_off;   // element offsets: member stride, offset of this step
     int32_t *sweeps;         // [count] or null
     unsigned long long *nonfinite;
+    long long *prof;         // optional [gridDim.x][16] phase cycle counters (NNS_STREAM_PROF=1)
 };
 
-struct Coef {
-    double ca, cb, cc, cu, cv, beta, tol;
-};
+// phase timers: thread `lead` of a role accumulates clock64() deltas into prof[slot]
+#define NNS_PROF_T() (a.prof ? clock64() : 0ll)
+#define NNS_PROF_ADD(slot, t0) do { if (a.prof && lead) a.prof[(size_t)blockIdx.x * 16 + (slot)] += clock64() - (t0); } while (0)
 
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -75,6 +78,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *b, int count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
     asm volatile(
@@ -101,85 +107,44 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// |d| <= tol decided on the INTEGER pipe (the FP64 pipe is the bottleneck of the sweeps): for finite
-// doubles the magnitude order equals the order of the bit patterns; NaN patterns exceed every finite
-// one, so NaN counts as "not converged", like !(fabs(d) <= tol).
-__device__ __forceinline__ bool exceeds_bits(double d, unsigned long long tolbits) {
-    return ((unsigned long long)__double_as_longlong(d) & 0x7fffffffffffffffull) > tolbits;
-}
+__constant__ short c_ord[128];     // diag_ord of cell q = li * BC + lj (host-filled; used by the stencil role)
 
-template <int BR, int BC>
-struct SHalo {
-    const double *hN, *hS, *hW, *hE;
-    double *Hme;
-    bool pubT, pubB, pubL, pubR;
-};
-
-// One lexicographic sweep over the thread's own block (all operands in registers), then publication
-// of the block perimeter for the neighbours (see chorin_fd_chip.cu for the ordering argument).
-template <int BR, int BC, bool TRACK>
-__device__ __forceinline__ bool block_sweep(double (&P)[BR][BC], const double2 *__restrict__ Cme, const SHalo<BR, BC> &h,
-                                            const Coef &k, unsigned long long tolbits) {
-    double hn[BC], hs[BC], hw[BR], he[BR];
-#pragma unroll
-    for (int lj = 0; lj < BC; ++lj) { hn[lj] = h.hN[lj * NT_SOR]; hs[lj] = h.hS[lj * NT_SOR]; }
-#pragma unroll
-    for (int li = 0; li < BR; ++li) { hw[li] = h.hW[li * NT_SOR]; he[li] = h.hE[li * NT_SOR]; }
-    bool viol = false;
-#pragma unroll
-    for (int li = 0; li < BR; ++li) {
-#pragma unroll
-        for (int lj = 0; lj < BC; ++lj) {
-            const int q = li * BC + lj;
-            const double2 cc2 = Cme[(q >> 1) * NT_SOR];
-            const double cp = (q & 1) ? cc2.y : cc2.x;
-            const double n = li > 0 ? P[li - 1][lj] : hn[lj];
-            const double w = lj > 0 ? P[li][lj - 1] : hw[li];
-            const double s = li < BR - 1 ? P[li + 1][lj] : hs[lj];
-            const double e = lj < BC - 1 ? P[li][lj + 1] : he[li];
-            const double c = P[li][lj];
-            const double z = fma(k.ca, s, fma(k.cb, e, fma(-k.beta, c, -cp)));
-            const double d = fma(k.ca, n, fma(k.cb, w, z));
-            P[li][lj] = c + d;
-            if (TRACK) viol |= exceeds_bits(d, tolbits);
-        }
-    }
-#pragma unroll
-    for (int lj = 0; lj < BC; ++lj) {
-        if (h.pubT) h.Hme[lj * NT_SOR] = P[0][lj];
-        if (h.pubB) h.Hme[(BC + lj) * NT_SOR] = P[BR - 1][lj];
-    }
-#pragma unroll
-    for (int li = 0; li < BR; ++li) {
-        if (h.pubL) h.Hme[(2 * BC + li) * NT_SOR] = P[li][0];
-        if (h.pubR) h.Hme[(2 * BC + BR + li) * NT_SOR] = P[li][BC - 1];
-    }
-    return viol;
-}
-
-template <int BR, int BC, bool TRACK>
+// All sweeps of one member as a wavefront of SUB-blocks.  Every thread owns a BR x BC block of p and
+// sweeps it as two sub-blocks, rows [0, RS) and [RS, BR), in alternate super-stages: with sub-block row
+// index sbi = 2*bi + {0, 1}, sub-block (sbi, bj) performs sweep s at super-stage T = sbi + bj + 2s.  All
+// four lexicographic dependencies of a sub-block are then one super-stage old (north / west: same sweep,
+// south / east: previous sweep), the boundary between the two sub-blocks of a thread stays in registers,
+// and -- unlike a one-block-per-thread wavefront, where a thread idles every other super-stage -- every
+// thread works in every super-stage, so each SM sub-partition always has TWO warps to issue from.
+// sd = 2*bi + bj.  mask: bit s set = sweep s still violates the exit test; amb: bit s set = undecided by
+// the fast test (TRACK 1 only).
+template <int BR, int BC, int RS, int TRACK>
 __device__ __forceinline__ void wavefront(double (&P)[BR][BC], const double2 *Cme, const SHalo<BR, BC> &h, bool owner,
-                                          int bd, int tmax, int cap, const Coef &k, unsigned long long tolbits,
-                                          unsigned long long &mask) {
-    if (owner) {   // publish the whole perimeter once
-#pragma unroll
-        for (int lj = 0; lj < BC; ++lj) {
-            if (h.pubT) h.Hme[lj * NT_SOR] = P[0][lj];
-            if (h.pubB) h.Hme[(BC + lj) * NT_SOR] = P[BR - 1][lj];
-        }
-#pragma unroll
-        for (int li = 0; li < BR; ++li) {
-            if (h.pubL) h.Hme[(2 * BC + li) * NT_SOR] = P[li][0];
-            if (h.pubR) h.Hme[(2 * BC + BR + li) * NT_SOR] = P[li][BC - 1];
-        }
-    }
+                                          int sd, int tmax, int cap, const Coef &k, unsigned long long tolbits,
+                                          unsigned long long &mask, unsigned long long &amb, long long *prof = nullptr) {
+    if (owner) publish<BR, BC, 0, BR>(P, h);   // the whole perimeter once
     named_sync(BAR_SOR, NT_SOR);
+    const unsigned tolhi = (unsigned)(tolbits >> 32);
     for (int T = 0; T <= tmax; ++T) {
-        const int two_s = T - bd;
-        const bool work = owner && !(two_s & 1) && (unsigned)two_s <= (unsigned)(2 * (cap - 1));
+        const int q = T - sd;                       // 2s for the top sub-block, 2s + 1 for the bottom one
+        const bool work = owner && q >= 0 && q <= 2 * (cap - 1) + 1;
         if (work) {
-            const bool v = block_sweep<BR, BC, TRACK>(P, Cme, h, k, tolbits);
-            if (TRACK) mask |= (unsigned long long)v << (two_s >> 1);
+            unsigned mhi = 0u;
+            bool v = false;
+#ifdef NNS_STREAM_PROF_SWEEP
+            const long long ts0 = prof ? clock64() : 0ll;
+#endif
+            if (!(q & 1)) block_sweep<BR, BC, RS, 0, RS, TRACK>(P, Cme, h, k, tolbits, mhi, v);
+            else block_sweep<BR, BC, RS, RS, BR, TRACK>(P, Cme, h, k, tolbits, mhi, v);
+#ifdef NNS_STREAM_PROF_SWEEP
+            if (prof) { prof[0] += clock64() - ts0; prof[1] += 1; }
+#endif
+            if (TRACK == 1) {
+                mask |= (unsigned long long)(mhi > tolhi) << (q >> 1);
+                amb |= (unsigned long long)(mhi == tolhi) << (q >> 1);
+            } else if (TRACK == 2) {
+                mask |= (unsigned long long)v << (q >> 1);
+            }
         }
         named_sync(BAR_SOR, NT_SOR);
     }
@@ -214,40 +179,83 @@ struct Cfg {
     static constexpr size_t CS_BYTES = sizeof(double2) * NCH * NT_SOR;
     static constexpr size_t H_BYTES = sizeof(double) * NSLOT * NT_SOR;
     static constexpr size_t RING_BYTES = sizeof(double) * RING * 4 * NY;
-    static constexpr size_t ROWBUF_BYTES = sizeof(double) * 2 * NY;
-    static constexpr size_t SMEM_BYTES = CS_BYTES + H_BYTES + RING_BYTES + ROWBUF_BYTES;
+    static constexpr size_t SMEM_BYTES = CS_BYTES + H_BYTES + RING_BYTES;
     static_assert(NB <= NT_SOR, "one SOR thread per block");
     static_assert(NY == NT_ST, "the stencil role maps one thread to one column");
     static_assert((NY * sizeof(double)) % 16 == 0, "bulk copies need 16-byte rows");
 };
 
 // ----------------------------------------------------------------------------------------------
-// stencil role: row streamer.  Rows of F fields travel global -> smem ring by bulk copies issued by
-// one thread; row r of a pass has sequence number seq0 + r, slot = seq % RING, parity = (seq/RING)&1.
+// stencil role: row streamer.  Rows of F fields travel global -> shared memory in groups of GR rows;
+// a group of one field is contiguous in global memory, so it is ONE bulk copy (TMA unit) per field and
+// group (measured on B200: ~75 cycles of issue per bulk copy and ~200 per mbarrier round trip, so the
+// copies must be few and large -- scripts/micro/tma_ring.cu).  The ring holds NG = 2 groups (double
+// buffer); each group has a "full" mbarrier (transaction bytes) and an "empty" mbarrier (one arrival per
+// stencil warp).  Group g of a pass has sequence number g0 + g: slot = seq % NG, parity = (seq / NG) & 1.
+// There is NO CTA-wide barrier in the row loops: the four stencil warps only meet through the ring.
+// A row needs the row below it, so a step works on rows [GR*g - 1, GR*g + GR - 1): the east / west
+// operands of the lagging row GR*g - 1 are saved in registers before its group is released.
 // ----------------------------------------------------------------------------------------------
 template <int NY>
 struct Ring {
-    double *buf;          // [RING][4][NY]
-    uint64_t *full;       // [RING]
-    unsigned seq0;        // sequence number of row 0 of the current pass
+    double *buf;          // [NG][4][GR][NY]
+    uint64_t *full;       // [NG]
+    uint64_t *empty;      // [NG]
+    unsigned g0;          // sequence number of group 0 of the current pass
 
-    __device__ __forceinline__ double *row(unsigned r, int f) const { return buf + (((seq0 + r) % RING) * 4 + f) * NY; }
-    template <int F>
-    __device__ __forceinline__ void issue(unsigned r, const double *const (&src)[F]) const {
-        uint64_t *b = full + (seq0 + r) % RING;
-        mbar_expect_tx(b, F * NY * (uint32_t)sizeof(double));
-#pragma unroll
-        for (int f = 0; f < F; ++f) bulk_g2s(row(r, f), src[f] + (size_t)r * NY, NY * (uint32_t)sizeof(double), b);
+    // row r (0 <= r < GR) of field f of group g
+    __device__ __forceinline__ const double *row(unsigned g, int f, int r) const {
+        return buf + ((((g0 + g) % NG) * 4 + f) * GR + r) * NY;
     }
-    __device__ __forceinline__ void wait(unsigned r) const {
-        const unsigned seq = seq0 + r;
-        mbar_wait(full + seq % RING, (seq / RING) & 1u);
+    // producer lane: refill the slot of group g with rows [g*GR, g*GR+GR) of F fields
+    template <int F>
+    __device__ __forceinline__ void issue(unsigned g, const double *const (&src)[F]) const {
+        const unsigned seq = g0 + g;
+        if (seq >= (unsigned)NG) mbar_wait(empty + seq % NG, ((seq / NG) - 1u) & 1u);   // previous use consumed by all warps
+        uint64_t *b = full + seq % NG;
+        constexpr uint32_t bytes = (uint32_t)(GR * NY * sizeof(double));
+        mbar_expect_tx(b, F * bytes);
+#pragma unroll
+        for (int f = 0; f < F; ++f)
+            bulk_g2s(const_cast<double *>(row(g, f, 0)), src[f] + (size_t)g * GR * NY, bytes, b);
+    }
+    __device__ __forceinline__ void wait_full(unsigned g) const {
+        const unsigned seq = g0 + g;
+        mbar_wait(full + seq % NG, (seq / NG) & 1u);
+    }
+    __device__ __forceinline__ void release(unsigned g) const {     // whole warp: its reads of group g are done
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(empty + (g0 + g) % NG);
+    }
+    // every stencil thread pulls one 128-byte line of group g of F fields towards L2 (F*GR*NY*8/128 <= 128 lines)
+    template <int F>
+    __device__ __forceinline__ void prefetch_l2(unsigned g, const double *const (&src)[F], int ts) const {
+        constexpr int LPF = GR * NY * (int)sizeof(double) / 128;      // lines per field and group
+        if (ts < F * LPF) {
+            const int f = ts / LPF, l = ts - f * LPF;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(src[f] + (size_t)g * GR * NY) + l * 128));
+        }
     }
 };
 
+// C' = beta/den * (dx rho dy^2/dt (ui[i,j]-ui[i-1,j]) + dy rho dx^2/dt (vi[i,j]-vi[i,j-1]))  (chorin_fd:186-188)
+// stored at the position the owning SOR thread expects (image of its shared-memory chunks).
 template <typename C>
-__device__ void stencil_pass1(const StreamArgs &a, Ring<C::NY> &ring, double *rowbuf, int m, int ts, double *img) {
-    constexpr int NX = C::NX, NY = C::NY;
+__device__ __forceinline__ void store_cprime(double *img, const short *tidmap, const short *s_ord, int i, int j, double c) {
+    const int bi = (i - 1) / C::BRc, li = (i - 1) - bi * C::BRc;
+    const int bj = (j - 1) / C::BCc, lj = (j - 1) - bj * C::BCc;
+    const int t = tidmap[bi * C::NBCc + bj], q = s_ord[li * C::BCc + lj];
+    img[((size_t)(q >> 1) * NT_SOR + t) * 2 + (q & 1)] = c;
+}
+
+// pass 1: predictor of member m -> un, vn (global) and the C' image.
+template <typename C>
+__device__ void stencil_pass1(const StreamArgs &a, Ring<C::NY> &ring, const short *s_ord, int m, int ts, double *img) {
+#ifdef NNS_ABL_NOSTENCIL      // timing ablation: the SOR role alone on the SM
+    return;
+#endif
+    constexpr int NX = C::NX, NY = C::NY, NGROUPS = NX / GR;
+    static_assert(NX % GR == 0, "rows must fill whole ring groups");
     const size_t N = (size_t)NX * NY;
     const double *src[4] = {a.uc + m * N, a.vc + m * N, a.up + m * N, a.vp + m * N};
     double *un = a.un + m * N, *vn = a.vn + m * N;
@@ -255,12 +263,16 @@ __device__ void stencil_pass1(const StreamArgs &a, Ring<C::NY> &ring, double *ro
     const double *bcval = a.bcval ? a.bcval + (size_t)m * a.n_bcs : nullptr;
     const double dt = a.g.dt, dx = a.g.dx, dy = a.g.dy, rho = a.g.rho, beta = a.g.beta;
     const double dx2 = dx * dx, dy2 = dy * dy;
-    const double r2dx = 1.0 / (2.0 * dx), r2dy = 1.0 / (2.0 * dy), rdx2 = 1.0 / dx2, rdy2 = 1.0 / dy2;
+    // u' = u - dt (3/2 Adv(u^n) - 1/2 Adv(u^{n-1})) + dt nu (3/2 Lap(u^n) - 1/2 Lap(u^{n-1}))  (chorin_fd:63-91)
+    // with every constant folded into one coefficient per term (36 FP64 operations per cell)
+    const double a0x = 1.5 * dt / (2.0 * dx), a0y = 1.5 * dt / (2.0 * dy);     // AB2 weights of the advection speeds
+    const double a1x = 0.5 * dt / (2.0 * dx), a1y = 0.5 * dt / (2.0 * dy);
+    const double c0x = 1.5 * dt * nu / dx2, c0y = 1.5 * dt * nu / dy2;         // AB2 weights of the Laplacians
+    const double c1x = 0.5 * dt * nu / dx2, c1y = 0.5 * dt * nu / dy2;
     const double den = 2.0 * dx2 + 2.0 * dy2;
     const double cc = beta / den, cu = dx * rho * dy2 / dt, cv = dy * rho * dx2 / dt;
-    const int j = ts;
+    const int j = ts, lane = ts & 31;
     const bool jin = j > 0 && j < NY - 1;
-    // column part of the C' image address (block column, column inside the block)
     const int bj = jin ? (j - 1) / C::BCc : 0, lj = jin ? (j - 1) - bj * C::BCc : 0;
 
     // pull the next member's pressure towards L2 while we are at it (the SOR role loads it soon)
@@ -269,78 +281,100 @@ __device__ void stencil_pass1(const StreamArgs &a, Ring<C::NY> &ring, double *ro
         for (size_t off = (size_t)ts * 128; off < N * sizeof(double); off += (size_t)NT_ST * 128)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + off));
     }
-
-    if (ts == 0)
-        for (unsigned r = 0; r < (unsigned)RING && r < (unsigned)NX; ++r) ring.template issue<4>(r, src);
+    if (ts == 0) { ring.template issue<4>(0, src); ring.template issue<4>(1, src); }
+    ring.template prefetch_l2<4>(2, src, ts);
+    ring.template prefetch_l2<4>(3, src, ts);
 
     double uN = 0, uC = 0, uS = 0, vN = 0, vC = 0, vS = 0, aN = 0, aC = 0, aS = 0, bN = 0, bC = 0, bS = 0;
+    double uE = 0, uW = 0, vE = 0, vW = 0, aE = 0, aW = 0, bE = 0, bW = 0;   // east / west operands of the current row
     double ru_prev = 0.0;
-    ring.wait(0);
-    uS = ring.row(0, 0)[j]; vS = ring.row(0, 1)[j]; aS = ring.row(0, 2)[j]; bS = ring.row(0, 3)[j];
-    for (int i = 0; i < NX; ++i) {
-        uN = uC; vN = vC; aN = aC; bN = bC;
-        uC = uS; vC = vS; aC = aS; bC = bS;
-        if (i + 1 < NX) {
-            ring.wait(i + 1);
-            uS = ring.row(i + 1, 0)[j]; vS = ring.row(i + 1, 1)[j]; aS = ring.row(i + 1, 2)[j]; bS = ring.row(i + 1, 3)[j];
-        }
+    int bi = 0, li = -1, tsor = 0;           // block row / row inside the block of the current row, owning SOR thread
+
+    // one row: (uC..) is row i, (uS..) row i+1, (uE, uW..) the east / west neighbours of row i
+    auto do_row = [&](int i) {
         double ru = uC, rv = vC;
         const bool interior = jin && i > 0 && i < NX - 1;
         if (interior) {
-            const double *ur = ring.row(i, 0), *vr = ring.row(i, 1), *ar = ring.row(i, 2), *br = ring.row(i, 3);
-            const double uE = ur[j + 1], uW = ur[j - 1], vE = vr[j + 1], vW = vr[j - 1];
-            const double pE = ar[j + 1], pW = ar[j - 1], qE = br[j + 1], qW = br[j - 1];
             // both advection terms difference along axis 0 (chorin_fd:74,76,83,85)
-            const double k0 = uC * r2dx + vC * r2dy, k1 = aC * r2dx + bC * r2dy;
-            const double advu = 1.5 * (k0 * (uS - uN)) - 0.5 * (k1 * (aS - aN));
-            const double advv = 1.5 * (k0 * (vS - vN)) - 0.5 * (k1 * (bS - bN));
-            const double lapu = 1.5 * ((uS - 2.0 * uC + uN) * rdx2 + (uE - 2.0 * uC + uW) * rdy2) -
-                                0.5 * ((aS - 2.0 * aC + aN) * rdx2 + (pE - 2.0 * aC + pW) * rdy2);
-            const double lapv = 1.5 * ((vS - 2.0 * vC + vN) * rdx2 + (vE - 2.0 * vC + vW) * rdy2) -
-                                0.5 * ((bS - 2.0 * bC + bN) * rdx2 + (qE - 2.0 * bC + qW) * rdy2);
-            ru = uC - dt * advu + (dt * nu) * lapu;
-            rv = vC - dt * advv + (dt * nu) * lapv;
+            const double k0 = fma(uC, a0x, vC * a0y), k1 = fma(aC, a1x, bC * a1y);
+            const double lu = fma(-2.0, uC, uS + uN), mu = fma(-2.0, uC, uE + uW);
+            const double la = fma(-2.0, aC, aS + aN), ma = fma(-2.0, aC, aE + aW);
+            const double lv = fma(-2.0, vC, vS + vN), mv = fma(-2.0, vC, vE + vW);
+            const double lb = fma(-2.0, bC, bS + bN), mb = fma(-2.0, bC, bE + bW);
+            ru = fma(-c1y, ma, fma(-c1x, la, fma(c0y, mu, fma(c0x, lu, fma(k1, aS - aN, fma(-k0, uS - uN, uC))))));
+            rv = fma(-c1y, mb, fma(-c1x, lb, fma(c0y, mv, fma(c0x, lv, fma(k1, bS - bN, fma(-k0, vS - vN, vC))))));
         }
         un[(size_t)i * NY + j] = ru;
         vn[(size_t)i * NY + j] = rv;
-        rowbuf[(i & 1) * NY + j] = rv;
-        named_sync(BAR_ST, NT_ST);          // row i consumed by everyone: its ring slot is free, rowbuf is complete
-        if (ts == 0 && i + RING < NX) ring.template issue<4>(i + RING, src);
-        if (interior) {
-            // C' = beta/den * (dx rho dy^2/dt (ui[i,j]-ui[i-1,j]) + dy rho dx^2/dt (vi[i,j]-vi[i,j-1]))   (:186-188);
-            // row 1 / column 1 use pre-BC edge values here and are patched after the BC pass
-            const double rv_w = rowbuf[(i & 1) * NY + j - 1];
-            const double c = cc * (cu * (ru - ru_prev) + cv * (rv - rv_w));
-            const int bi = (i - 1) / C::BRc, li = (i - 1) - bi * C::BRc;
-            const int t = a.tidmap[bi * C::NBCc + bj], q = li * C::BCc + lj;
-            img[((size_t)(q >> 1) * NT_SOR + t) * 2 + (q & 1)] = c;
+        // vi of the western neighbour: the lane below (lane 0 of a warp has no such lane: its column, like
+        // row 1 and column 1 whose operands are boundary lines, is patched after the BC pass)
+        const double rv_w = __shfl_up_sync(0xffffffffu, rv, 1);
+        if (i >= 1 && i < NX - 1) {
+            if (++li == C::BRc) { li = 0; ++bi; }
+            if (li == 0 && jin) tsor = a.tidmap[bi * C::NBCc + bj];
+            if (jin && lane > 0) {
+                const double c = cc * (cu * (ru - ru_prev) + cv * (rv - rv_w));
+                const int q = s_ord[li * C::BCc + lj];
+                img[((size_t)(q >> 1) * NT_SOR + tsor) * 2 + (q & 1)] = c;
+            }
         }
         ru_prev = ru;
+    };
+    const int jw = j > 0 ? j - 1 : j, je = j < NY - 1 ? j + 1 : j;
+    for (int g = 0; g < NGROUPS; ++g) {
+        ring.wait_full(g);
+#pragma unroll
+        for (int r = -1; r < GR - 1; ++r) {              // rows GR*g - 1 .. GR*g + GR - 2
+            const int i = g * GR + r;
+            // shift the window: row i becomes current, row i+1 (slot row r+1 of this group) is loaded
+            uN = uC; vN = vC; aN = aC; bN = bC;
+            uC = uS; vC = vS; aC = aS; bC = bS;
+            uS = ring.row(g, 0, r + 1)[j]; vS = ring.row(g, 1, r + 1)[j]; aS = ring.row(g, 2, r + 1)[j]; bS = ring.row(g, 3, r + 1)[j];
+            if (r >= 0) {                                  // east / west of row i: in this group (r == -1: saved registers)
+                uE = ring.row(g, 0, r)[je]; uW = ring.row(g, 0, r)[jw]; vE = ring.row(g, 1, r)[je]; vW = ring.row(g, 1, r)[jw];
+                aE = ring.row(g, 2, r)[je]; aW = ring.row(g, 2, r)[jw]; bE = ring.row(g, 3, r)[je]; bW = ring.row(g, 3, r)[jw];
+            }
+            if (i >= 0) do_row(i);
+        }
+        // east / west of the group's last row, needed by the next step after this slot is refilled
+        uE = ring.row(g, 0, GR - 1)[je]; uW = ring.row(g, 0, GR - 1)[jw]; vE = ring.row(g, 1, GR - 1)[je]; vW = ring.row(g, 1, GR - 1)[jw];
+        aE = ring.row(g, 2, GR - 1)[je]; aW = ring.row(g, 2, GR - 1)[jw]; bE = ring.row(g, 3, GR - 1)[je]; bW = ring.row(g, 3, GR - 1)[jw];
+        ring.release(g);
+        if (g + 2 < NGROUPS) {
+            if (ts == 0) ring.template issue<4>(g + 2, src);
+            if (g + 4 < NGROUPS) ring.template prefetch_l2<4>(g + 4, src, ts);
+        }
     }
-    ring.seq0 += NX;
+    uN = uC; vN = vC; uC = uS; vC = vS;                    // last row (an edge: copied)
+    do_row(NX - 1);
+    ring.g0 += NGROUPS;
     __threadfence_block();
     named_sync(BAR_ST, NT_ST);
     st_apply_bc_global(un, NX, NY, a.ubc, bcval, dx, dy, ts);
     st_apply_bc_global(vn, NX, NY, a.vbc, bcval, dx, dy, ts);
-    // patch C' on row 1 (thread j) and column 1 (thread i), which read the boundary lines
-    if (jin) {
-        const double c = cc * (cu * (un[(size_t)NY + j] - un[j]) + cv * (vn[(size_t)NY + j] - vn[(size_t)NY + j - 1]));
-        const int t = a.tidmap[bj], q = lj;
-        img[((size_t)(q >> 1) * NT_SOR + t) * 2 + (q & 1)] = c;
-    }
+    // patch C' where an operand is a boundary line (row 1, column 1) or belongs to another warp's lane 31
+    auto patch = [&](int i, int jj) {
+        const size_t gq = (size_t)i * NY + jj;
+        const double c = cc * (cu * (un[gq] - un[gq - NY]) + cv * (vn[gq] - vn[gq - 1]));
+        store_cprime<C>(img, a.tidmap, s_ord, i, jj, c);
+    };
+    if (jin) patch(1, j);
     for (int i = 2 + ts; i < NX - 1; i += NT_ST) {
-        const size_t g = (size_t)i * NY + 1;
-        const double c = cc * (cu * (un[g] - un[g - NY]) + cv * (vn[g] - vn[g - 1]));
-        const int bi = (i - 1) / C::BRc, li = (i - 1) - bi * C::BRc;
-        const int t = a.tidmap[bi * C::NBCc], q = li * C::BCc;
-        img[((size_t)(q >> 1) * NT_SOR + t) * 2 + (q & 1)] = c;
+        patch(i, 1);
+#pragma unroll
+        for (int w = 1; w < NT_ST / 32; ++w)
+            if (32 * w < NY - 1) patch(i, 32 * w);
     }
     __threadfence();                      // the image is pulled through L2 (cp.async.cg) by the SOR role
 }
 
+// pass 2: p_bc, projection and trajectory snapshot of member m.
 template <typename C>
 __device__ void stencil_pass2(const StreamArgs &a, Ring<C::NY> &ring, int m, int ts) {
-    constexpr int NX = C::NX, NY = C::NY;
+#ifdef NNS_ABL_NOSTENCIL
+    return;
+#endif
+    constexpr int NX = C::NX, NY = C::NY, NGROUPS = NX / GR;
     const size_t N = (size_t)NX * NY;
     double *pg = a.p + m * N, *un = a.un + m * N, *vn = a.vn + m * N;
     const double *bcval = a.bcval ? a.bcval + (size_t)m * a.n_bcs : nullptr;
@@ -351,37 +385,45 @@ __device__ void stencil_pass2(const StreamArgs &a, Ring<C::NY> &ring, int m, int
     const double *src[3] = {pg, un, vn};
     const int j = ts;
     const bool jin = j > 0 && j < NY - 1;
+    const int jw = j > 0 ? j - 1 : j, je = j < NY - 1 ? j + 1 : j;
     const double kx = dt / (2.0 * dx), ky = dt / (2.0 * dy);
     const size_t toff = (size_t)m * a.traj_member_stride + a.traj_off;
     if (ts == 0) {
         fence_proxy_async();
-        for (unsigned r = 0; r < (unsigned)RING && r < (unsigned)NX; ++r) ring.template issue<3>(r, src);
+        ring.template issue<3>(0, src);
+        ring.template issue<3>(1, src);
     }
-    double pN = 0, pC = 0, pS = 0;
+    double pN = 0, pC = 0, pS = 0, pE = 0, pW = 0, ruC = 0, rvC = 0, ruS = 0, rvS = 0;
     unsigned long long bad = 0;
-    ring.wait(0);
-    pS = ring.row(0, 0)[j];
-    for (int i = 0; i < NX; ++i) {
-        pN = pC; pC = pS;
-        if (i + 1 < NX) {
-            ring.wait(i + 1);
-            pS = ring.row(i + 1, 0)[j];
-        }
-        double ru = ring.row(i, 1)[j], rv = ring.row(i, 2)[j];
+    auto do_row = [&](int i) {
+        double ru = ruC, rv = rvC;
         const size_t q = (size_t)i * NY + j;
         if (jin && i > 0 && i < NX - 1) {
-            const double *pr = ring.row(i, 0);
             ru -= kx * (pS - pN);
-            rv -= ky * (pr[j + 1] - pr[j - 1]);
+            rv -= ky * (pE - pW);
             un[q] = ru;
             vn[q] = rv;
         }
         if (a.traj_u) { a.traj_u[toff + q] = ru; a.traj_v[toff + q] = rv; a.traj_p[toff + q] = pC; }
         if (a.flags & NNS_FLAG_CHECK_FINITE) bad += !(isfinite(ru) && isfinite(rv) && isfinite(pC));
-        named_sync(BAR_ST, NT_ST);
-        if (ts == 0 && i + RING < NX) ring.template issue<3>(i + RING, src);
+    };
+    for (int g = 0; g < NGROUPS; ++g) {
+        ring.wait_full(g);
+#pragma unroll
+        for (int r = -1; r < GR - 1; ++r) {
+            const int i = g * GR + r;
+            pN = pC; pC = pS; ruC = ruS; rvC = rvS;
+            pS = ring.row(g, 0, r + 1)[j]; ruS = ring.row(g, 1, r + 1)[j]; rvS = ring.row(g, 2, r + 1)[j];
+            if (r >= 0) { pE = ring.row(g, 0, r)[je]; pW = ring.row(g, 0, r)[jw]; }
+            if (i >= 0) do_row(i);
+        }
+        pE = ring.row(g, 0, GR - 1)[je]; pW = ring.row(g, 0, GR - 1)[jw];
+        ring.release(g);
+        if (ts == 0 && g + 2 < NGROUPS) ring.template issue<3>(g + 2, src);
     }
-    ring.seq0 += NX;
+    pN = pC; pC = pS; ruC = ruS; rvC = rvS;
+    do_row(NX - 1);
+    ring.g0 += NGROUPS;
     if ((a.flags & NNS_FLAG_CHECK_FINITE) && bad) atomicAdd(a.nonfinite, bad);
 }
 
@@ -389,20 +431,21 @@ __device__ void stencil_pass2(const StreamArgs &a, Ring<C::NY> &ring, int m, int
 template <int BR, int BC, int NBR, int NBC>
 struct CfgX : Cfg<BR, BC, NBR, NBC> {
     static constexpr int BRc = BR, BCc = BC, NBRc = NBR, NBCc = NBC;
+    static constexpr int RSc = (BR + 1) / 2;       // rows of the top sub-block
 };
 
 template <typename C>
 __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const StreamArgs a) {
-    constexpr int BR = C::BRc, BC = C::BCc, NX = C::NX, NY = C::NY, NCH = C::NCH;
+    constexpr int BR = C::BRc, BC = C::BCc, RS = C::RSc, NX = C::NX, NY = C::NY, NCH = C::NCH;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ unsigned long long s_mask;
+    __shared__ unsigned long long s_mask[2];
     __shared__ int s_need;
-    __shared__ __align__(8) uint64_t s_full[RING];
+    __shared__ __align__(8) uint64_t s_full[NG], s_empty[NG];
+    __shared__ short s_ord[128];          // split_ord of cell li * BC + lj (copy of c_ord: per-lane indices)
 
     double2 *Cs = reinterpret_cast<double2 *>(smem_raw);
     double *H = reinterpret_cast<double *>(smem_raw + C::CS_BYTES);
     double *ringbuf = reinterpret_cast<double *>(smem_raw + C::CS_BYTES + C::H_BYTES);
-    double *rowbuf = reinterpret_cast<double *>(smem_raw + C::CS_BYTES + C::H_BYTES + C::RING_BYTES);
 
     const int tid = threadIdx.x;
     const size_t N = (size_t)NX * NY;
@@ -410,10 +453,11 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
     double *img = a.cimg + (size_t)blockIdx.x * 2 * NCH * NT_SOR;
 
     if (tid == 0) {
-        for (int r = 0; r < RING; ++r) mbar_init(&s_full[r], 1);
+        for (int r = 0; r < NG; ++r) { mbar_init(&s_full[r], 1); mbar_init(&s_empty[r], NT_ST / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_mask = 0ull;
+        s_mask[0] = 0ull; s_mask[1] = 0ull;
     }
+    if (tid < 128) s_ord[tid] = c_ord[tid];
     __syncthreads();
     if (nmine == 0) return;
 
@@ -421,25 +465,36 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
         // =============================== stencil role ===========================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_ST));
         const int ts = tid - NT_SOR;
-        Ring<NY> ring{ringbuf, s_full, 0u};
-        stencil_pass1<C>(a, ring, rowbuf, blockIdx.x, ts, img);
+        Ring<NY> ring{ringbuf, s_full, s_empty, 0u};
+        const bool lead = ts == 0;
+        long long t0 = NNS_PROF_T();
+        stencil_pass1<C>(a, ring, s_ord, blockIdx.x, ts, img);
+        NNS_PROF_ADD(8, t0);
         named_arrive(BAR_READY + 0, NT_SOR + NT_ST);
         for (int k = 0; k < nmine; ++k) {
             const int m = blockIdx.x + k * gridDim.x;
             if (k + 1 < nmine) {
+                t0 = NNS_PROF_T();
                 named_sync(BAR_CONSUMED + (k & 1), NT_SOR + NT_ST);       // the SOR role has pulled image k
-                stencil_pass1<C>(a, ring, rowbuf, m + gridDim.x, ts, img);
+                NNS_PROF_ADD(9, t0);
+                t0 = NNS_PROF_T();
+                stencil_pass1<C>(a, ring, s_ord, m + gridDim.x, ts, img);
+                NNS_PROF_ADD(8, t0);
                 named_arrive(BAR_READY + ((k + 1) & 1), NT_SOR + NT_ST);
             }
+            t0 = NNS_PROF_T();
             named_sync(BAR_DONE + (k & 1), NT_SOR + NT_ST);               // SOR of member k finished, p written
+            NNS_PROF_ADD(10, t0);
+            t0 = NNS_PROF_T();
             stencil_pass2<C>(a, ring, m, ts);
+            NNS_PROF_ADD(11, t0);
         }
     } else {
         // ================================= SOR role =============================================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_SOR));
-        const bool owner = tid < C::NB;
-        SBlock ds{1, 1, -1, -1, -1, -1, 0, 0};
-        if (owner) ds = a.desc[tid];
+        SBlock ds = a.desc[tid];
+        const bool owner = ds.r0 > 0;
+        if (!owner) { ds.r0 = 1; ds.c0 = 1; }
         const int r0 = ds.r0, c0 = ds.c0;
         SHalo<BR, BC> h;
         h.Hme = H + tid;
@@ -453,10 +508,10 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
         const double dx = a.g.dx, dy = a.g.dy, beta = a.g.beta;
         const double dx2 = dx * dx, dy2 = dy * dy, den = 2.0 * dx2 + 2.0 * dy2;
         Coef k;
-        k.ca = beta * dy2 / den; k.cb = beta * dx2 / den; k.cc = 0; k.cu = 0; k.cv = 0; k.beta = beta; k.tol = a.g.tol;
+        k.ca = beta * dy2 / den; k.cb = beta * dx2 / den; k.cc = -beta; k.cu = 0; k.cv = 0; k.beta = beta; k.tol = a.g.tol;
         const unsigned long long tolbits = (unsigned long long)__double_as_longlong(a.g.tol);
         const int cap = a.g.nit - 1;
-        const int tmax = C::NBRc + C::NBCc - 2 + 2 * (cap - 1);
+        const int tmax = 2 * C::NBRc + C::NBCc - 2 + 2 * (cap - 1);      // last sub-block diagonal + 2 (cap - 1)
 
         for (int kk = 0; kk < nmine; ++kk) {
             const int m = blockIdx.x + kk * gridDim.x;
@@ -468,6 +523,8 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
 #pragma unroll
                     for (int lj = 0; lj < BC; ++lj) P[li][lj] = owner ? pg[(size_t)(r0 + li) * NY + c0 + lj] : 0.0;
             };
+            const bool lead = tid == 0;
+            long long t0 = NNS_PROF_T();
             load_block();                          // p is not touched by the stencil role before SOR finishes
             if (owner) {                           // frozen boundary values into the unread own slots
 #pragma unroll
@@ -481,39 +538,69 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
                     if (!h.pubR) h.Hme[(2 * BC + BR + li) * NT_SOR] = pg[(size_t)(r0 + li) * NY + c0 + BC];
                 }
             }
+            NNS_PROF_ADD(0, t0);
+            t0 = NNS_PROF_T();
             named_sync(BAR_READY + (kk & 1), NT_SOR + NT_ST);            // C' image of member kk is complete
+            NNS_PROF_ADD(1, t0);
+            t0 = NNS_PROF_T();
             {
                 const double2 *gi = reinterpret_cast<const double2 *>(img) + tid;
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) cp_async16(Cs + c * NT_SOR + tid, gi + c * NT_SOR);
                 cp_async_wait_all();
             }
-            if (tid == 0) s_mask = 0ull;
             named_sync(BAR_SOR, NT_SOR);
             if (kk + 1 < nmine) named_arrive(BAR_CONSUMED + (kk & 1), NT_SOR + NT_ST);
+            NNS_PROF_ADD(2, t0);
+            t0 = NNS_PROF_T();
 
             int need = 0;
             if (cap > 0) {
-                unsigned long long mask = 0ull;
-                wavefront<BR, BC, true>(P, Cme, h, owner, ds.bd, tmax, cap, k, tolbits, mask);
-                unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)mask);
-                unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(mask >> 32));
-                if ((tid & 31) == 0) atomicOr(&s_mask, ((unsigned long long)hi << 32) | lo);
-                named_sync(BAR_SOR, NT_SOR);
-                if (tid == 0) {
-                    const unsigned long long full = cap >= 64 ? ~0ull : ((1ull << cap) - 1ull);
-                    const unsigned long long clr = ~s_mask & full;
-                    s_need = clr ? __ffsll((long long)clr) : cap;
+                // reduce the per-thread sweep flags to the number of sweeps the reference loop runs;
+                // returns -1 if the fast test left the deciding sweep undecided
+                auto sweeps_needed = [&](unsigned long long mask, unsigned long long amb) -> int {
+                    unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)mask);
+                    unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(mask >> 32));
+                    unsigned alo = __reduce_or_sync(0xffffffffu, (unsigned)amb);
+                    unsigned ahi = __reduce_or_sync(0xffffffffu, (unsigned)(amb >> 32));
+                    if ((tid & 31) == 0) {
+                        atomicOr(&s_mask[0], ((unsigned long long)hi << 32) | lo);
+                        atomicOr(&s_mask[1], ((unsigned long long)ahi << 32) | alo);
+                    }
+                    named_sync(BAR_SOR, NT_SOR);
+                    if (tid == 0) {
+                        const unsigned long long full = cap >= 64 ? ~0ull : ((1ull << cap) - 1ull);
+                        const unsigned long long viol = s_mask[0], und = s_mask[1] & ~viol & full;
+                        const unsigned long long clr = ~viol & full;       // sweeps without a certain violation
+                        int nd = clr ? __ffsll((long long)clr) : cap;      // first such sweep: s + 1 sweeps run
+                        // the first sweep without a certain violation decides; if it is merely undecided, redo exactly
+                        if (clr && ((und >> (nd - 1)) & 1ull)) nd = -1;
+                        s_need = nd;
+                        s_mask[0] = 0ull; s_mask[1] = 0ull;
+                    }
+                    named_sync(BAR_SOR, NT_SOR);
+                    return s_need;
+                };
+                unsigned long long mask = 0ull, amb = 0ull;
+                wavefront<BR, BC, RS, 1>(P, Cme, h, owner, ds.bd, tmax, cap, k, tolbits, mask, amb,
+                                     a.prof && (tid == 0 || tid == 128) ? a.prof + (size_t)blockIdx.x * 16 + 12 + (tid >> 6) : nullptr);
+                NNS_PROF_ADD(3, t0);
+                t0 = NNS_PROF_T();
+                need = sweeps_needed(mask, amb);
+                if (need < 0) {
+                    // max|dp| of the deciding sweep shares its high word with tol: repeat with the exact test
+                    load_block();
+                    mask = 0ull; amb = 0ull;
+                    wavefront<BR, BC, RS, 2>(P, Cme, h, owner, ds.bd, tmax, cap, k, tolbits, mask, amb);
+                    need = sweeps_needed(mask, 0ull);
                 }
-                named_sync(BAR_SOR, NT_SOR);
-                need = s_need;
                 if (need < cap) {
                     // the sequential loop would have stopped after `need` sweeps: redo from the
                     // untouched global p with the sweep count capped (rare: near steady state)
                     load_block();
-                    unsigned long long dummy = 0ull;
-                    wavefront<BR, BC, false>(P, Cme, h, owner, ds.bd, C::NBRc + C::NBCc - 2 + 2 * (need - 1), need, k,
-                                             tolbits, dummy);
+                    unsigned long long d0 = 0ull, d1 = 0ull;
+                    wavefront<BR, BC, RS, 0>(P, Cme, h, owner, ds.bd, 2 * C::NBRc + C::NBCc - 2 + 2 * (need - 1), need, k, tolbits,
+                                         d0, d1);
                 }
             }
             if (owner) {
@@ -522,9 +609,12 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
 #pragma unroll
                     for (int lj = 0; lj < BC; ++lj) pg[(size_t)(r0 + li) * NY + c0 + lj] = P[li][lj];
             }
+            NNS_PROF_ADD(4, t0);
+            t0 = NNS_PROF_T();
             if (a.sweeps && tid == 0) a.sweeps[m] = need;
             __threadfence();              // p is re-read by the stencil role, partly through the TMA unit
             named_arrive(BAR_DONE + (kk & 1), NT_SOR + NT_ST);
+            NNS_PROF_ADD(5, t0);
         }
     }
 }
@@ -536,7 +626,9 @@ struct StreamPlan {
     std::vector<short> tidmap;
     void *d_tab = nullptr;      // desc then tidmap
     double *d_img = nullptr;
+    long long *d_prof = nullptr;
     int grid = 0;
+    bool ok = false;
 };
 
 template <typename C>
@@ -545,19 +637,30 @@ static void build_tables(StreamPlan &pl) {
     struct Item { int key, bi, bj; };
     std::vector<Item> items;
     for (int bi = 0; bi < NBR; ++bi)
-        for (int bj = 0; bj < NBC; ++bj) items.push_back({bi + bj, bi, bj});
-    // blocks of one parity work in the same super-stage: keep them in the same warps, ordered by diagonal
+        for (int bj = 0; bj < NBC; ++bj) items.push_back({2 * bi + bj, bi, bj});     // key = top sub-block diagonal
+    // threads whose top sub-blocks work in the same super-stages (same parity of the key, i.e. of bj) share
+    // warps, ordered by diagonal so that a warp's lanes enter and leave the active band together
     std::stable_sort(items.begin(), items.end(), [](const Item &x, const Item &y) {
         if ((x.key & 1) != (y.key & 1)) return (x.key & 1) < (y.key & 1);
         return x.key != y.key ? x.key < y.key : x.bj < y.bj;
     });
-    std::vector<int> tid_of((size_t)NB);
-    for (int t = 0; t < NB; ++t) tid_of[(size_t)items[t].bi * NBC + items[t].bj] = t;
-    pl.desc.assign(NT_SOR, SBlock{1, 1, -1, -1, -1, -1, 0, 0});
+    // even-parity blocks occupy threads [0, n_even), odd-parity blocks start at thread NT_SOR/2: a warp never
+    // mixes parities, and each SM sub-partition hosts one warp of either parity (top and bottom sub-block
+    // sweeps have different lengths; together they balance)
+    int n_even = 0;
+    for (const Item &it : items) n_even += !(it.key & 1);
+    std::vector<int> tid_of((size_t)NB), thr((size_t)NB);
+    for (int t = 0; t < NB; ++t) {
+        thr[t] = t < n_even ? t : NT_SOR / 2 + (t - n_even);
+        tid_of[(size_t)items[t].bi * NBC + items[t].bj] = thr[t];
+    }
+    pl.desc.assign(NT_SOR, SBlock{0, 0, -1, -1, -1, -1, 0, 0});     // r0 == 0 marks a thread without a block
     pl.tidmap.resize(NB);
     for (int t = 0; t < NB; ++t) pl.tidmap[t] = (short)tid_of[t];
-    for (int t = 0; t < NB; ++t) {
-        const int bi = items[t].bi, bj = items[t].bj;
+    pl.ok = n_even <= NT_SOR / 2 && NB - n_even <= NT_SOR / 2;
+    for (int it = 0; it < NB; ++it) {
+        const int t = thr[it];
+        const int bi = items[it].bi, bj = items[it].bj;
         SBlock d;
         d.r0 = (short)(1 + BR * bi);
         d.c0 = (short)(1 + BC * bj);
@@ -565,13 +668,32 @@ static void build_tables(StreamPlan &pl) {
         d.nS = bi < NBR - 1 ? (short)tid_of[(size_t)(bi + 1) * NBC + bj] : (short)-1;
         d.nW = bj > 0 ? (short)tid_of[(size_t)bi * NBC + bj - 1] : (short)-1;
         d.nE = bj < NBC - 1 ? (short)tid_of[(size_t)bi * NBC + bj + 1] : (short)-1;
-        d.bd = (short)(bi + bj);
+        d.bd = (short)(2 * bi + bj);
         d.pad = 0;
         pl.desc[t] = d;
     }
 }
 
 }  // namespace
+
+// Debug aid: print and reset the phase counters (NNS_STREAM_PROF=1), averaged over CTAs.
+void chorin_stream_prof_dump(nns_handle *h) {
+    StreamPlan *pl = static_cast<StreamPlan *>(h->stream_plan);
+    if (!pl || !pl->d_prof) return;
+    std::vector<long long> v((size_t)16 * pl->grid);
+    cudaDeviceSynchronize();
+    cudaMemcpy(v.data(), pl->d_prof, sizeof(long long) * v.size(), cudaMemcpyDeviceToHost);
+    cudaMemset(pl->d_prof, 0, sizeof(long long) * v.size());
+    static const char *nm[16] = {"sor.load_p", "sor.wait_ready", "sor.pull_cimg", "sor.wavefront", "sor.reduce_redo",
+                                 "sor.store_p", "", "", "st.pass1", "st.wait_consumed", "st.wait_done", "st.pass2",
+                                 "sor.sweep_cyc(t0)", "sor.sweeps(t0)", "sor.sweep_cyc(t128)", "sor.sweeps(t128)"};
+    for (int k = 0; k < 16; ++k) {
+        if (!nm[k][0]) continue;
+        double s = 0;
+        for (int b = 0; b < pl->grid; ++b) s += (double)v[(size_t)b * 16 + k];
+        fprintf(stderr, "[nns stream prof] %-18s %12.0f cycles/CTA\n", nm[k], s / pl->grid);
+    }
+}
 
 bool chorin_stream_eligible(const nns_handle *h, int phases, int nsteps) {
     const char *e = getenv("NNS_CHIP_MODE");
@@ -586,6 +708,7 @@ void chorin_stream_free(nns_handle *h) {
     if (!pl) return;
     cudaFree(pl->d_tab);
     cudaFree(pl->d_img);
+    cudaFree(pl->d_prof);
     delete pl;
     h->stream_plan = nullptr;
 }
@@ -606,6 +729,14 @@ int chorin_stream_step(nns_handle *h, const double *uc, const double *vc, const 
         NNS_CUDA(cudaMalloc(&pl->d_tab, dbytes + tbytes));
         NNS_CUDA(cudaMemcpy(pl->d_tab, pl->desc.data(), dbytes, cudaMemcpyHostToDevice));
         NNS_CUDA(cudaMemcpy(static_cast<char *>(pl->d_tab) + dbytes, pl->tidmap.data(), tbytes, cudaMemcpyHostToDevice));
+        short ord[128] = {0};
+        for (int li = 0; li < C::BRc; ++li)
+            for (int lj = 0; lj < C::BCc; ++lj) ord[li * C::BCc + lj] = (short)split_ord<C::BRc, C::BCc, C::RSc>(li, lj);
+        NNS_CUDA(cudaMemcpyToSymbol(c_ord, ord, sizeof(ord)));
+        if (getenv("NNS_STREAM_PROF")) {
+            NNS_CUDA(cudaMalloc(&pl->d_prof, sizeof(long long) * 16 * h->sm_count));
+            NNS_CUDA(cudaMemset(pl->d_prof, 0, sizeof(long long) * 16 * h->sm_count));
+        }
         pl->grid = h->sm_count;
         NNS_CUDA(cudaMalloc(&pl->d_img, sizeof(double2) * C::NCH * NT_SOR * (size_t)pl->grid));
         NNS_CUDA(cudaMemset(pl->d_img, 0, sizeof(double2) * C::NCH * NT_SOR * (size_t)pl->grid));
@@ -628,6 +759,7 @@ int chorin_stream_step(nns_handle *h, const double *uc, const double *vc, const 
     a.traj_member_stride = traj_member_stride; a.traj_off = traj_off;
     a.sweeps = sweeps;
     a.nonfinite = h->d_nonfinite;
+    a.prof = pl->d_prof;
     const int grid = count < pl->grid ? count : pl->grid;
     chorin_stream_kernel<C><<<grid, NT_SOR + NT_ST, C::SMEM_BYTES, st>>>(a);
     NNS_CUDA(cudaGetLastError());

@@ -1,0 +1,150 @@
+// sor_block.cuh -- the register-block SOR sweep shared by chorin_fd_stream.cu and the sweep
+// microbenchmark (scripts/micro/sweep_bench.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace nns {
+
+constexpr int NT_SOR = 256;     // threads of the SOR role (2 warpgroups); stride of the smem tables
+
+struct Coef {
+    double ca, cb, cc, cu, cv, beta, tol;
+};
+
+// |d| <= tol decided on the INTEGER pipe (the FP64 pipe is the bottleneck of the sweeps): for finite
+// doubles the magnitude order equals the order of the bit patterns; NaN patterns exceed every finite
+// one, so NaN counts as "not converged", like !(fabs(d) <= tol).
+__device__ __forceinline__ bool exceeds_bits(double d, unsigned long long tolbits) {
+    return ((unsigned long long)__double_as_longlong(d) & 0x7fffffffffffffffull) > tolbits;
+}
+
+template <int BR, int BC>
+struct SHalo {
+    const double *hN, *hS, *hW, *hE;
+    double *Hme;
+    bool pubT, pubB, pubL, pubR;
+};
+
+// Publish the perimeter cells of rows [R0, R1) of the block into the thread's halo slots
+// ([0,BC) top row, [BC,2BC) bottom row, [2BC,2BC+BR) left column, [2BC+BR,2BC+2BR) right column);
+// slots facing a physical boundary hold the frozen boundary values of p and are never republished.
+template <int BR, int BC, int R0, int R1>
+__device__ __forceinline__ void publish(const double (&P)[BR][BC], const SHalo<BR, BC> &h) {
+#pragma unroll
+    for (int lj = 0; lj < BC; ++lj) {
+        if (R0 == 0 && h.pubT) h.Hme[lj * NT_SOR] = P[0][lj];
+        if (R1 == BR && h.pubB) h.Hme[(BC + lj) * NT_SOR] = P[BR - 1][lj];
+    }
+#pragma unroll
+    for (int li = R0; li < R1; ++li) {
+        if (h.pubL) h.Hme[(2 * BC + li) * NT_SOR] = P[li][0];
+        if (h.pubR) h.Hme[(2 * BC + BR + li) * NT_SOR] = P[li][BC - 1];
+    }
+}
+
+// Position of cell (li, lj) of an R x BC (sub-)block in ANTI-DIAGONAL-major order (diagonal li + lj, then
+// li): the order in which a sweep consumes the right-hand side.
+template <int R, int BC>
+__host__ __device__ constexpr int diag_ord(int li, int lj) {
+    const int kd = li + lj;
+    int o = 0;
+    for (int t = 0; t < kd; ++t) {
+        const int lo = t - (BC - 1) > 0 ? t - (BC - 1) : 0, hi = t < R - 1 ? t : R - 1;
+        o += hi - lo + 1;
+    }
+    const int lo = kd - (BC - 1) > 0 ? kd - (BC - 1) : 0;
+    return o + (li - lo);
+}
+
+// Layout of the C' chunks of a thread whose BR x BC block is swept as two sub-blocks, rows [0, RS) and
+// [RS, BR): the cells of the top sub-block in its diagonal order, then those of the bottom one.
+template <int BR, int BC, int RS>
+__host__ __device__ constexpr int split_ord(int li, int lj) {
+    return li < RS ? diag_ord<RS, BC>(li, lj) : RS * BC + diag_ord<BR - RS, BC>(li - RS, lj);
+}
+
+// One sweep over rows [R0, R1) of the thread's own BR x BC block (the block is swept as two sub-blocks
+// in alternate super-stages, see chorin_fd_stream.cu), all operands in registers, then publication of
+// that sub-block's part of the perimeter for the neighbouring threads.
+// Inside the sub-block the lexicographic order of the reference is executed as an anti-diagonal
+// wavefront: cells of one diagonal only depend on the previous diagonal (north, west: new values)
+// and on later diagonals (south, east: old values), so the result is the sequential one, while the
+// instruction stream carries up to min(R1-R0, BC) independent dependency chains (the FP64 pipe has an
+// 8-cycle latency and a 2-cycle issue interval per warp).
+//   stage A (old operands):  base = ca*s + cb*e - beta*c - C'
+//   stage B (new operands):  d = ca*n + cb*w + base, p += d     (2 dependent DFMAs + 1 DADD per cell)
+// North of row R0 is the thread's own row R0-1 (already swept this sweep) or the halo of the block above;
+// south of row R1-1 is the own row R1 (not yet swept) or the halo of the block below.
+// TRACK: 0 none; 1 fast: running maximum of the high words of |p' - p| on the integer pipe (decides
+// "max|dp| <= tol" unless the maximum shares its high word with tol: ambiguous, resolved by an exact
+// re-run); 2 exact 64-bit comparison per cell.
+template <int BR, int BC, int RS, int R0, int R1, int TRACK>
+__device__ __forceinline__ void block_sweep(double (&P)[BR][BC], const double2 *__restrict__ Cme, const SHalo<BR, BC> &h,
+                                            const Coef &k, unsigned long long tolbits, unsigned &mhi, bool &viol) {
+#ifdef NNS_ABL_NOCOMPUTE
+    publish<BR, BC, R0, R1>(P, h);
+    return;
+#endif
+    constexpr int NR = R1 - R0, ND = NR + BC - 1;
+    double base[2][NR];
+    auto stageA = [&](int kd, double (&out)[NR]) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int lj = kd - r, li = R0 + r;
+            if (lj >= 0 && lj < BC) {
+                const int o = split_ord<BR, BC, RS>(li, lj);
+#ifdef NNS_ABL_NOCPRIME      // timing ablations (scripts/ablate.sh): results are wrong on purpose
+                const double cp = 1e-3 * o;
+#else
+                const double2 cc2 = Cme[(o >> 1) * NT_SOR];
+                const double cp = (o & 1) ? cc2.y : cc2.x;
+#endif
+#ifdef NNS_ABL_NOHALO
+                const double s = li < BR - 1 ? P[li + 1][lj] : 0.5;
+                const double e = lj < BC - 1 ? P[li][lj + 1] : 0.25;
+#else
+                const double s = li < BR - 1 ? P[li + 1][lj] : h.hS[lj * NT_SOR];
+                const double e = lj < BC - 1 ? P[li][lj + 1] : h.hE[li * NT_SOR];
+#endif
+                out[r] = fma(k.ca, s, fma(k.cb, e, fma(k.cc, P[li][lj], -cp)));      // k.cc = -beta (1 - beta with NNS_SOR_FORM_PN)
+            }
+        }
+    };
+    stageA(0, base[0]);
+#pragma unroll
+    for (int kd = 0; kd < ND; ++kd) {
+        if (kd + 1 < ND) stageA(kd + 1, base[(kd + 1) & 1]);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int lj = kd - r, li = R0 + r;
+            if (lj >= 0 && lj < BC) {
+#ifdef NNS_ABL_NOHALO
+                const double n = li > 0 ? P[li - 1][lj] : 0.125;
+                const double w = lj > 0 ? P[li][lj - 1] : 0.375;
+#else
+                const double n = li > 0 ? P[li - 1][lj] : h.hN[lj * NT_SOR];
+                const double w = lj > 0 ? P[li][lj - 1] : h.hW[li * NT_SOR];
+#endif
+#ifdef NNS_SOR_FORM_PN       // p' in 5 DFMAs, d = p' - p for the exit test (shorter chain, but needs register moves)
+                const double pn = fma(k.ca, n, fma(k.cb, w, base[kd & 1][r]));
+                if (TRACK) {
+                    const double d = pn - P[li][lj];
+                    if (TRACK == 1) mhi = max(mhi, (unsigned)__double2hiint(d) & 0x7fffffffu);
+                    else viol |= exceeds_bits(d, tolbits);
+                }
+                P[li][lj] = pn;
+#else                       // d in 5 DFMAs, p += d in place (no register renaming at the loop back-edge)
+                const double d = fma(k.ca, n, fma(k.cb, w, base[kd & 1][r]));
+                if (TRACK == 1) mhi = max(mhi, (unsigned)__double2hiint(d) & 0x7fffffffu);
+                if (TRACK == 2) viol |= exceeds_bits(d, tolbits);
+                P[li][lj] += d;
+#endif
+            }
+        }
+    }
+#ifndef NNS_ABL_NOPUBLISH
+    publish<BR, BC, R0, R1>(P, h);
+#endif
+}
+
+}  // namespace nns

@@ -1,0 +1,80 @@
+// sweep_bench.cu -- isolates the register-block SOR sweep of chorin_fd_stream.cu: W warps per SM run
+// block_sweep<9,7> back to back out of shared memory (no barriers, no neighbours), optionally next to
+// "noise" warps that issue FP64 work like the stencil role does.  Reports cycles per block sweep.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I../../neural-navier-stokes_b200/csrc sweep_bench.cu
+#include <stdio.h>
+#include "sor_block.cuh"
+using namespace nns;
+
+template <int TRACK, int R0, int R1>
+__global__ void __launch_bounds__(256, 1) bench(double *out, long long *cyc, int iters, int nsweep_warps, int noise_warps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *Cs = reinterpret_cast<double2 *>(smem_raw);
+    double *H = reinterpret_cast<double *>(smem_raw + sizeof(double2) * 32 * NT_SOR);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int q = tid; q < 32 * NT_SOR; q += blockDim.x) { Cs[q] = make_double2(1e-3 * q, 2e-3 * q); H[q] = 1e-4 * q; }
+    __syncthreads();
+    if (warp < nsweep_warps) {
+        double P[9][7];
+#pragma unroll
+        for (int li = 0; li < 9; ++li)
+#pragma unroll
+            for (int lj = 0; lj < 7; ++lj) P[li][lj] = 0.01 * (li + lj) + tid;
+        SHalo<9, 7> h;
+        h.Hme = H + tid; h.pubT = h.pubB = h.pubL = h.pubR = true;
+        h.hN = H + 7 * NT_SOR + ((tid + 1) & 255); h.hS = H + ((tid + 2) & 255);
+        h.hW = H + 23 * NT_SOR + ((tid + 3) & 255); h.hE = H + 14 * NT_SOR + ((tid + 4) & 255);
+        Coef k; k.ca = 0.3125; k.cb = 0.3125; k.cc = -1.25; k.beta = 1.25; k.tol = 5e-6;
+        unsigned mhi = 0; bool v = false;
+        const long long t0 = clock64();
+        #pragma unroll 1
+        for (int it = 0; it < iters; ++it) block_sweep<9, 7, 5, R0, R1, TRACK>(P, Cs + tid, h, k, 0x3ed4f8b588e368f1ull, mhi, v);
+        const long long t1 = clock64();
+        if ((tid & 31) == 0) cyc[blockIdx.x * 16 + warp] = t1 - t0;
+        double s = mhi + v;
+#pragma unroll
+        for (int li = 0; li < 9; ++li)
+#pragma unroll
+            for (int lj = 0; lj < 7; ++lj) s += P[li][lj];
+        if (s == 1.2345) out[0] = s;
+    } else if (warp < nsweep_warps + noise_warps) {
+        double x0 = tid, x1 = tid + 1, x2 = tid + 2, x3 = tid + 3;
+        for (int it = 0; it < iters * 40; ++it) {     // ~160 DFMA per sweep-equivalent
+            x0 = fma(x0, 1.0000001, 1e-9); x1 = fma(x1, 1.0000001, 1e-9);
+            x2 = fma(x2, 1.0000001, 1e-9); x3 = fma(x3, 1.0000001, 1e-9);
+        }
+        if (x0 + x1 + x2 + x3 == 1.2345) out[1] = x0;
+    }
+}
+
+template <int TRACK, int R0, int R1>
+static void run(double *out, long long *cyc, size_t smem, int nw, int noise) {
+    const int iters = 2000;
+    long long h[16];
+    cudaFuncSetAttribute(bench<TRACK, R0, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaMemset(cyc, 0, sizeof(long long) * 16 * 148);
+    bench<TRACK, R0, R1><<<148, 256, smem>>>(out, cyc, iters, nw, noise);
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    double mx = 0;
+    for (int w = 0; w < nw; ++w) mx = h[w] > mx ? h[w] : mx;
+    printf("TRACK %d rows [%d,%d) (%d cells) sweep warps/SM %d noise warps %d: %.0f cycles per sweep, %.1f per cell-warp/SMSP\n", TRACK, R0, R1,
+           (R1 - R0) * 7, nw, noise, mx / iters, mx / iters / ((R1 - R0) * 7) / ((nw + 3) / 4));
+}
+
+int main() {
+    double *out; long long *cyc;
+    cudaMalloc(&out, 64); cudaMalloc(&cyc, sizeof(long long) * 16 * 148);
+    const size_t smem = sizeof(double2) * 32 * NT_SOR + sizeof(double) * 32 * NT_SOR;
+    for (int nw : {1, 4, 8}) {
+        run<1, 0, 9>(out, cyc, smem, nw, 0);
+        run<1, 0, 5>(out, cyc, smem, nw, 0);
+        run<1, 5, 9>(out, cyc, smem, nw, 0);
+        run<0, 0, 9>(out, cyc, smem, nw, 0);
+        run<0, 0, 5>(out, cyc, smem, nw, 0);
+    }
+    run<1, 0, 9>(out, cyc, smem, 4, 4);
+    run<1, 0, 5>(out, cyc, smem, 4, 4);
+    printf("last error: %s\n", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
