@@ -587,6 +587,9 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
                 NNS_PROF_ADD(3, t0);
                 t0 = NNS_PROF_T();
                 need = sweeps_needed(mask, amb);
+#ifdef NNS_ABL_NOSTENCIL
+                need = cap;
+#endif
                 if (need < 0) {
                     // max|dp| of the deciding sweep shares its high word with tol: repeat with the exact test
                     load_block();
