@@ -183,6 +183,36 @@ int32_t nns_spectral_run(nns_handle *h, double *u, double *v, double *u1, double
 int32_t nns_spectral_run_host(nns_handle *h, double *u, double *v, double *u1, double *v1, double *p,
                               int32_t nsteps, double *traj_u, double *traj_v, double *traj_p);
 
+/* ---- chorin_fd on row slabs: ONE grid split over the GPUs of a box (new capability; the reference runs one
+ * process) ---------------------------------------------------------------------------------------
+ * Rank g owns the contiguous global rows [row0, row0 + nrows) (whole SOR tile rows; rank 0 also owns row 0,
+ * the last rank row nx-1) and stores every field as [nrows + 2][ny]: one halo row above and below its rows.
+ * nns_create is called with the GLOBAL nx, ny and batch = 1.  The lexicographic SOR of
+ * src/chorin_fd/simulate.py:183-200 runs as a hyperplane of tiles across all slabs, neighbouring ranks swap
+ * single rows of p over NCCL after every tick; results equal the single-GPU / reference results. */
+
+/* Partition (pure host logic): rows owned by `rank`.  tile_rows <= 0 selects the library default. */
+int32_t nns_slab_partition(int32_t nx, int32_t nranks, int32_t rank, int32_t tile_rows, int32_t *row0,
+                           int32_t *nrows);
+/* Tick plan (pure host logic): out8 = {tile rows TR, tile columns TC, nI, nJ, I0, I1, Ilo, Ihi}: the tile grid, the
+ * tile rows [I0, I1) of `rank`, and the tile rows [Ilo, Ihi] it sweeps at (tick, sweep) -- empty if Ihi < Ilo.
+ * Tile (I, J) performs sweep s at tick I + J + 2s; J = tick - 2*sweep - I. */
+int32_t nns_slab_plan(int32_t nx, int32_t ny, int32_t nranks, int32_t rank, int32_t tile_rows, int32_t tick,
+                      int32_t sweep, int32_t *out8);
+/* The BC list of `field` in list order on a local slab (src/boundary.py:34-86; _init_variables :236-249). */
+int32_t nns_slab_apply_bc(nns_handle *h, int32_t field, double *a, void *stream);
+/* 128-byte NCCL id: rank 0 creates it and hands it to the other ranks (e.g. torch.distributed broadcast). */
+int32_t nns_nccl_unique_id(uint8_t *id128);
+/* Attach the handle to its slab; creates the NCCL communicator when nranks > 1 (collective call). */
+int32_t nns_slab_attach(nns_handle *h, int32_t rank, int32_t nranks, const uint8_t *id128);
+/* Swap the boundary rows of one local field with the neighbouring ranks (fills the halo rows). */
+int32_t nns_slab_exchange(nns_handle *h, double *field, void *stream);
+/* One time step (step(), chorin_fd/simulate.py:212-234) on the local slabs.  Halo rows of u, v, u1, v1, p must be
+ * valid on entry (nns_slab_exchange once after initialisation); they are valid on return for u_out, v_out, p.
+ * sweeps_out_host: host int32 or NULL.  The call synchronises the stream once (exit-test decision). */
+int32_t nns_chorin_fd_slab_step(nns_handle *h, const double *u, const double *v, const double *u1, const double *v1,
+                                double *p, double *u_out, double *v_out, int32_t *sweeps_out_host, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,13 @@ _PROTOS = {
     "nns_chorin_fd_correct": (_i32, [_vp] * 7),
     "nns_direct_fd_run": (_i32, [_vp] * 4 + [_i32] + [_vp] * 4),
     "nns_direct_fd_run_host": (_i32, [_vp] * 4 + [_i32] + [_vp] * 3),
+    "nns_slab_partition": (_i32, [_i32, _i32, _i32, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
+    "nns_slab_plan": (_i32, [_i32] * 7 + [C.POINTER(_i32)]),
+    "nns_slab_apply_bc": (_i32, [_vp, _i32, _vp, _vp]),
+    "nns_nccl_unique_id": (_i32, [_vp]),
+    "nns_slab_attach": (_i32, [_vp, _i32, _i32, _vp]),
+    "nns_slab_exchange": (_i32, [_vp, _vp, _vp]),
+    "nns_chorin_fd_slab_step": (_i32, [_vp] * 10),
     "nns_spectral_set_operators": (_i32, [_vp, C.POINTER(_vp), _i32]),
     "nns_spectral_predictor": (_i32, [_vp] * 8),
     "nns_spectral_correct": (_i32, [_vp] * 9),

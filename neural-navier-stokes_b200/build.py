@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("NNS_B200_LIB") or os.path.join(HERE, "libnns_b200.so")   # override: experiments only
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "--cudart", "static"]
+              "-Xcompiler", "-fPIC", "-shared", "--cudart", "static", "-ldl"]
 
 
 def _nvcc():

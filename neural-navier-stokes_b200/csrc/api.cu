@@ -33,10 +33,19 @@ int chorin_stream_step(nns_handle *h, const double *uc, const double *vc, const 
                        double *un, double *vn, double *p, double *tu, double *tv, double *tp,
                        size_t traj_member_stride, size_t traj_off, int32_t *sweeps, cudaStream_t st, int m0,
                        int count);
-// chorin_fd_tiled.cu
+// chorin_fd_slab.cu
 int chorin_tiled_run(nns_handle *h, double *bufU[3], double *bufV[3], double *p, int nsteps, int nsteps_total,
                      int step0, int phases, int fixup, double *tu, double *tv, double *tp, int32_t *sweeps,
                      cudaStream_t st, int m0, int count);
+int slab_partition(int nx, int nranks, int rank, int tile_rows, int *row0, int *nrows, int *I0, int *I1, int *nI);
+void slab_free(nns_handle *h);
+int slab_plan(int nx, int ny, int nranks, int rank, int tile_rows, int T, int s, int *out);
+int slab_apply_bc(nns_handle *h, int field, double *a, cudaStream_t st);
+int slab_unique_id(unsigned char *id128);
+int slab_attach(nns_handle *h, int rank, int nranks, const unsigned char *id128);
+int slab_exchange(nns_handle *h, double *f, cudaStream_t st);
+int slab_step(nns_handle *h, const double *u, const double *v, const double *u1, const double *v1, double *p,
+              double *un, double *vn, int32_t *sweeps_host, cudaStream_t st);
 // direct_fd.cu
 int direct_run(nns_handle *h, double *u, double *v, double *p, int nsteps, double *tu, double *tv, double *tp,
                cudaStream_t st);
@@ -191,6 +200,7 @@ int32_t nns_destroy(nns_handle *h) {
     cudaFree(h->d_sweeps); cudaFree(h->d_nonfinite); cudaFree(h->d_blockdesc);
     chorin_chip_free_plan(h);
     chorin_stream_free(h);
+    slab_free(h);
     spectral_destroy(h);
     for (int k = 0; k < 4; ++k) cudaFree(h->d_scratch[k]);
     for (int k = 0; k < 7; ++k) cudaFree(h->d_stage[k]);
@@ -498,6 +508,49 @@ int32_t nns_spectral_run_host(nns_handle *h, double *u, double *v, double *u1, d
         }
     }
     return rc;
+}
+
+// ---- chorin_fd on row slabs (one grid over several GPUs) ---------------------------------------
+
+int32_t nns_slab_partition(int32_t nx, int32_t nranks, int32_t rank, int32_t tile_rows, int32_t *row0, int32_t *nrows) {
+    return slab_partition(nx, nranks, rank, tile_rows, row0, nrows, nullptr, nullptr, nullptr);
+}
+
+int32_t nns_slab_plan(int32_t nx, int32_t ny, int32_t nranks, int32_t rank, int32_t tile_rows, int32_t tick, int32_t sweep,
+                      int32_t *out8) {
+    if (!out8) { set_error("nns_slab_plan: null argument"); return NNS_ERR_INVALID; }
+    return slab_plan(nx, ny, nranks, rank, tile_rows, tick, sweep, out8);
+}
+
+int32_t nns_slab_apply_bc(nns_handle *h, int32_t field, double *a, void *stream) {
+    NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_FD);
+    if (!a || field < 0 || field > 2) { set_error("nns_slab_apply_bc: bad argument"); return NNS_ERR_INVALID; }
+    return slab_apply_bc(h, field, a, (cudaStream_t)stream);
+}
+
+int32_t nns_nccl_unique_id(uint8_t *id128) {
+    if (!id128) { set_error("nns_nccl_unique_id: null argument"); return NNS_ERR_INVALID; }
+    return slab_unique_id(id128);
+}
+
+int32_t nns_slab_attach(nns_handle *h, int32_t rank, int32_t nranks, const uint8_t *id128) {
+    NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_FD);
+    if (nranks < 1 || rank < 0 || rank >= nranks) { set_error("nns_slab_attach: bad rank %d of %d", rank, nranks); return NNS_ERR_INVALID; }
+    return slab_attach(h, rank, nranks, id128);
+}
+
+int32_t nns_slab_exchange(nns_handle *h, double *field, void *stream) {
+    NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_FD);
+    if (!field) { set_error("nns_slab_exchange: null field"); return NNS_ERR_INVALID; }
+    return slab_exchange(h, field, (cudaStream_t)stream);
+}
+
+int32_t nns_chorin_fd_slab_step(nns_handle *h, const double *u, const double *v, const double *u1, const double *v1,
+                                double *p, double *u_out, double *v_out, int32_t *sweeps_out_host, void *stream) {
+    NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_FD);
+    if (!u || !v || !u1 || !v1 || !p || !u_out || !v_out) { set_error("nns_chorin_fd_slab_step: null field"); return NNS_ERR_INVALID; }
+    if (u_out == u || u_out == u1 || v_out == v || v_out == v1) { set_error("nns_chorin_fd_slab_step: outputs alias inputs"); return NNS_ERR_INVALID; }
+    return slab_step(h, u, v, u1, v1, p, u_out, v_out, sweeps_out_host, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,533 @@
+// chorin_fd_slab.cu -- chorin_fd (explicit) for grids whose pressure field does NOT fit one SM: fields stay
+// in HBM, the exact lexicographic SOR runs as a HYPERPLANE of tiles, and one grid can be split into ROW SLABS
+// over the GPUs of a box (one process per GPU, NCCL send/recv of single halo rows over NVLink).
+//
+// Reference semantics (src/chorin_fd/simulate.py of mhw32/neural-navier-stokes): predictor :63-91, u/v BCs
+// :221-225, right-hand side :186-188, lexicographic SOR with early exit :183-200, p BCs :230-231, projection
+// :204-210.
+//
+// SOR.  The interior is cut into tiles of TR rows x TC = 32*LC columns.  Tile (I, J) performs sweep s at
+// tick T = I + J + 2s: its lexicographic predecessors -- tile (I-1, J) and (I, J-1) at the same sweep, tile
+// (I+1, J) and (I, J+1) at the previous sweep -- ran at tick T-1, and no two tiles of one tick touch, so one
+// kernel launch per tick executes every tile of the hyperplane (up to nit-1 sweeps in flight) and the result
+// is the sequential one.  Inside a tile ONE WARP pipelines the rows across its lanes: lane l owns LC columns
+// and works on row k at step k + l; the freshly updated west value arrives from lane l-1 by shuffle, the
+// north values are the lane's own previous results (registers), south / east / centre are still old in
+// memory.  No shared memory, no intra-tile barrier, exact order.
+// The sweeps are not temporally blocked (24 B per cell and sweep from HBM), see DESIGN.md 4.5.
+//
+// Slabs.  Rank g owns whole tile rows (plus the physical boundary rows at the ends) and stores its rows with
+// one halo row above and below.  All ranks run the same global tick loop; after every tick neighbouring
+// ranks swap their boundary rows of p (the row above supplies "north, same sweep", the row below "south,
+// previous sweep").  u, v, the predictor output and the final p swap halo rows once per step.  The per-sweep
+// exit flags are max-reduced over the ranks, so every rank takes the reference's early-exit decision.
+#include <dlfcn.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "nns_common.cuh"
+
+namespace nns {
+
+namespace {
+
+// ---- NCCL through dlopen (the library a torch process already loaded, else the system one) -------------
+typedef struct { char internal[128]; } NcclId;
+typedef void *NcclComm;
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(NcclId *) = nullptr;
+    int (*CommInitRank)(NcclComm *, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    int (*Send)(const void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+constexpr int kNcclInt32 = 2, kNcclFloat64 = 8, kNcclMax = 2;
+
+NcclApi *nccl_api() {
+    static NcclApi api;
+    if (api.lib) return &api;
+    const char *names[] = {getenv("NNS_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        if (!n || !n[0]) continue;
+        api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) { set_error("cannot load NCCL (libnccl.so.2): %s", dlerror()); return nullptr; }
+#define NNS_SYM(f)                                                                                     \
+    *reinterpret_cast<void **>(&api.f) = dlsym(api.lib, "nccl" #f);                                    \
+    if (!api.f) { set_error("NCCL symbol nccl" #f " not found"); api.lib = nullptr; return nullptr; }
+    NNS_SYM(GetUniqueId) NNS_SYM(CommInitRank) NNS_SYM(CommDestroy) NNS_SYM(Send) NNS_SYM(Recv) NNS_SYM(AllReduce)
+    NNS_SYM(GroupStart) NNS_SYM(GroupEnd) NNS_SYM(GetErrorString)
+#undef NNS_SYM
+    return &api;
+}
+
+#define NNS_NCCL(call)                                                                                 \
+    do {                                                                                               \
+        int r__ = (call);                                                                              \
+        if (r__ != 0) {                                                                                \
+            set_error("%s failed: %s", #call, nccl_api()->GetErrorString(r__));                        \
+            return NNS_ERR_CUDA;                                                                       \
+        }                                                                                              \
+    } while (0)
+
+constexpr int LC = 4, TC = 32 * LC;       // columns per lane / per tile
+
+struct SlabState {
+    int rank = 0, nranks = 1;
+    int row0 = 0, nrows = 0;      // owned global rows [row0, row0 + nrows)
+    int TR = 128;                 // tile rows
+    int nI = 0, nJ = 0;           // global tile grid over the interior
+    int I0 = 0, I1 = 0;           // owned tile rows
+    NcclComm comm = nullptr;
+    double *d_cprime = nullptr, *d_p0 = nullptr;    // [nrows + 2][ny]
+    double *d_own[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // single-GPU run(): haloed copies
+    int *d_flags = nullptr;       // [64] per-sweep "not converged" flags
+    int *h_flags = nullptr;       // pinned
+};
+
+struct SlabView {                 // addressing of the local slab of a field: element (i, j) of the GLOBAL grid
+    int rowbase;                  // global index of the first stored row (the top halo row)
+    int ny;
+    __host__ __device__ size_t at(int i, int j) const { return (size_t)(i - rowbase) * ny + j; }
+};
+
+int tile_rows_for(int nx) {
+    const char *e = getenv("NNS_SLAB_TR");
+    if (e && atoi(e) > 0) return atoi(e);
+    return nx >= 1024 ? 128 : 16;
+}
+
+// ---- kernels ----------------------------------------------------------------------------------------
+struct SlabGeom {
+    int nx, ny;                   // global grid
+    int row0, row1;               // owned rows [row0, row1)
+    SlabView v;
+    double dt, dx, dy, rho, nu, beta, tol;
+};
+
+// _explicit_predictor_step (chorin_fd:63-91): both advection terms difference along axis 0 (:74,76,83,85)
+__global__ void slab_predictor_kernel(SlabGeom g, const double *__restrict__ uc, const double *__restrict__ vc,
+                                      const double *__restrict__ up, const double *__restrict__ vp,
+                                      double *__restrict__ un, double *__restrict__ vn) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = g.row0 + blockIdx.y;
+    if (j >= g.ny || i >= g.row1) return;
+    const size_t q = g.v.at(i, j);
+    const int ny = g.ny;
+    const double u0 = uc[q], v0 = vc[q];
+    double ru = u0, rv = v0;
+    if (i > 0 && i < g.nx - 1 && j > 0 && j < ny - 1) {
+        const double dx2 = g.dx * g.dx, dy2 = g.dy * g.dy;
+        const double a0x = 1.5 * g.dt / (2.0 * g.dx), a0y = 1.5 * g.dt / (2.0 * g.dy);
+        const double a1x = 0.5 * g.dt / (2.0 * g.dx), a1y = 0.5 * g.dt / (2.0 * g.dy);
+        const double c0x = 1.5 * g.dt * g.nu / dx2, c0y = 1.5 * g.dt * g.nu / dy2;
+        const double c1x = 0.5 * g.dt * g.nu / dx2, c1y = 0.5 * g.dt * g.nu / dy2;
+        const double a0 = up[q], b0 = vp[q];
+        const double uS = uc[q + ny], uN = uc[q - ny], uE = uc[q + 1], uW = uc[q - 1];
+        const double vS = vc[q + ny], vN = vc[q - ny], vE = vc[q + 1], vW = vc[q - 1];
+        const double aS = up[q + ny], aN = up[q - ny], aE = up[q + 1], aW = up[q - 1];
+        const double bS = vp[q + ny], bN = vp[q - ny], bE = vp[q + 1], bW = vp[q - 1];
+        const double k0 = fma(u0, a0x, v0 * a0y), k1 = fma(a0, a1x, b0 * a1y);
+        const double lu = fma(-2.0, u0, uS + uN), mu = fma(-2.0, u0, uE + uW);
+        const double la = fma(-2.0, a0, aS + aN), ma = fma(-2.0, a0, aE + aW);
+        const double lv = fma(-2.0, v0, vS + vN), mv = fma(-2.0, v0, vE + vW);
+        const double lb = fma(-2.0, b0, bS + bN), mb = fma(-2.0, b0, bE + bW);
+        ru = fma(-c1y, ma, fma(-c1x, la, fma(c0y, mu, fma(c0x, lu, fma(k1, aS - aN, fma(-k0, uS - uN, u0))))));
+        rv = fma(-c1y, mb, fma(-c1x, lb, fma(c0y, mv, fma(c0x, lv, fma(k1, bS - bN, fma(-k0, vS - vN, v0))))));
+    }
+    un[q] = ru;
+    vn[q] = rv;
+}
+
+// one entry of a BC list on the owned rows (boundary.py:34-86); launched in list order
+__global__ void slab_bc_kernel(SlabGeom g, double *A, int side, int neumann, double value) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (side == NNS_SIDE_LEFT || side == NNS_SIDE_RIGHT) {
+        const int i = side == NNS_SIDE_LEFT ? 0 : g.nx - 1, in = side == NNS_SIDE_LEFT ? 1 : g.nx - 2;
+        if (i < g.row0 || i >= g.row1 || t >= g.ny) return;
+        const double sgn = side == NNS_SIDE_LEFT ? -g.dx : g.dx;
+        A[g.v.at(i, t)] = neumann ? A[g.v.at(in, t)] + sgn * value : value;
+    } else {
+        const int i = g.row0 + t;
+        if (i >= g.row1) return;
+        const int j = side == NNS_SIDE_BOTTOM ? 0 : g.ny - 1, jn = side == NNS_SIDE_BOTTOM ? 1 : g.ny - 2;
+        const double sgn = side == NNS_SIDE_BOTTOM ? -g.dy : g.dy;
+        A[g.v.at(i, j)] = neumann ? A[g.v.at(i, jn)] + sgn * value : value;
+    }
+}
+
+// pre-scaled right-hand side C' (chorin_fd:186-188)
+__global__ void slab_cprime_kernel(SlabGeom g, const double *__restrict__ ui, const double *__restrict__ vi,
+                                   double *__restrict__ cp) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = g.row0 + blockIdx.y;
+    if (j >= g.ny || i >= g.row1) return;
+    const size_t q = g.v.at(i, j);
+    double c = 0.0;
+    if (i > 0 && i < g.nx - 1 && j > 0 && j < g.ny - 1) {
+        const double dx2 = g.dx * g.dx, dy2 = g.dy * g.dy, den = 2.0 * dx2 + 2.0 * dy2;
+        const double cc = g.beta / den, cu = g.dx * g.rho * dy2 / g.dt, cv = g.dy * g.rho * dx2 / g.dt;
+        c = cc * (cu * (ui[q] - ui[q - g.ny]) + cv * (vi[q] - vi[q - 1]));
+    }
+    cp[q] = c;
+}
+
+// projection (chorin_fd:204-210) in place on (ui, vi), + optional snapshot / non-finite count
+__global__ void slab_project_kernel(SlabGeom g, const double *__restrict__ p, double *__restrict__ un,
+                                    double *__restrict__ vn, unsigned long long *nonfinite, int check) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = g.row0 + blockIdx.y;
+    if (j >= g.ny || i >= g.row1) return;
+    const size_t q = g.v.at(i, j);
+    double ru = un[q], rv = vn[q];
+    if (i > 0 && i < g.nx - 1 && j > 0 && j < g.ny - 1) {
+        ru -= g.dt / (2.0 * g.dx) * (p[q + g.ny] - p[q - g.ny]);
+        rv -= g.dt / (2.0 * g.dy) * (p[q + 1] - p[q - 1]);
+        un[q] = ru;
+        vn[q] = rv;
+    }
+    if (check && !(isfinite(ru) && isfinite(rv) && isfinite(p[q]))) atomicAdd(nonfinite, 1ull);
+}
+
+// Tile rows of sweep s that a rank owning tile rows [I0, I1) works on at tick T (tile (I, J) runs sweep s at
+// T = I + J + 2s, 0 <= J < nJ).  Shared by the kernel and the exported plan function.
+__host__ __device__ inline bool tick_tile_rows(int T, int s, int I0, int I1, int nJ, int *Ilo, int *Ihi) {
+    const int d = T - 2 * s;
+    if (d < 0) return false;
+    *Ilo = I0 > d - (nJ - 1) ? I0 : d - (nJ - 1);
+    *Ihi = I1 - 1 < d ? I1 - 1 : d;
+    return *Ilo <= *Ihi;
+}
+
+struct SweepArgs {
+    SlabGeom g;
+    int TR, nJ, I0, I1, cap;
+    double *p;
+    const double *cp;
+    int *flags;        // [cap] set to 1 when sweep s still violates the exit test; null = no tracking
+};
+
+// All tiles of hyperplane T (see the header).  blockIdx.y = sweep, 4 warps per CTA = 4 tiles.
+__global__ void __launch_bounds__(128) slab_sweep_kernel(const SweepArgs a, int T) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = blockIdx.y;
+    int Ilo, Ihi;
+    if (s >= a.cap || !tick_tile_rows(T, s, a.I0, a.I1, a.nJ, &Ilo, &Ihi)) return;
+    const int I = Ilo + blockIdx.x * 4 + warp;
+    if (I > Ihi) return;
+    const int J = T - 2 * s - I;
+    const SlabGeom &g = a.g;
+    const int ny = g.ny;
+    const int i0 = 1 + I * a.TR, i1 = min(i0 + a.TR, g.nx - 1);
+    const int nr = i1 - i0;
+    const int c0 = 1 + J * TC + lane * LC;
+    const int nc = max(0, min(LC, ny - 1 - c0));         // valid columns of this lane
+    const double dx2 = g.dx * g.dx, dy2 = g.dy * g.dy, den = 2.0 * dx2 + 2.0 * dy2;
+    const double ca = g.beta * dy2 / den, cb = g.beta * dx2 / den, mbeta = -g.beta, tol = g.tol;
+    double *P = a.p;
+    const double *CP = a.cp;
+
+    double pn[LC], pc[LC], ps[LC];
+    double wlast = 0.0;            // the lane's last updated value of the current row (west operand of lane + 1)
+    bool viol = false;
+#pragma unroll
+    for (int jj = 0; jj < LC; ++jj) { pn[jj] = 0.0; pc[jj] = 0.0; ps[jj] = 0.0; }
+    for (int tau = 0; tau < nr + 31; ++tau) {
+        const int k = tau - lane;
+        const bool act = nc > 0 && k >= 0 && k < nr;
+        const int i = i0 + k;
+        const double wsh = __shfl_up_sync(0xffffffffu, wlast, 1);      // lane - 1 finished row k one step ago
+        if (act) {
+            const size_t q = g.v.at(i, c0);
+            if (k == 0) {
+#pragma unroll
+                for (int jj = 0; jj < LC; ++jj)
+                    if (jj < nc) { pn[jj] = P[q - ny + jj]; pc[jj] = P[q + jj]; }
+            }
+            double cpv[LC];
+#pragma unroll
+            for (int jj = 0; jj < LC; ++jj)
+                if (jj < nc) { ps[jj] = P[q + ny + jj]; cpv[jj] = CP[q + jj]; }
+            const double east = P[q + nc];
+            double w = lane == 0 ? P[q - 1] : wsh;
+#pragma unroll
+            for (int jj = 0; jj < LC; ++jj)
+                if (jj < nc) {
+                    const double e = (jj + 1 < nc) ? pc[jj + 1] : east;
+                    const double z = fma(ca, ps[jj], fma(cb, e, fma(mbeta, pc[jj], -cpv[jj])));
+                    const double dd = fma(ca, pn[jj], fma(cb, w, z));
+                    viol |= !(fabs(dd) <= tol);
+                    w = pc[jj] + dd;
+                    P[q + jj] = w;
+                    pn[jj] = w;
+                    pc[jj] = ps[jj];
+                }
+            wlast = w;
+        }
+        __syncwarp();
+    }
+    if (a.flags && __any_sync(0xffffffffu, viol) && lane == 0) atomicOr(&a.flags[s], 1);
+}
+
+int exchange_rows(nns_handle *h, SlabState *S, double *f, cudaStream_t st) {
+    // swap boundary rows with the neighbouring ranks: local layout [nrows + 2][ny], halo rows first and last
+    if (S->nranks == 1) return NNS_OK;
+    NcclApi *N = nccl_api();
+    const int ny = h->g.ny;
+    double *top_halo = f, *first = f + ny, *last = f + (size_t)S->nrows * ny, *bot_halo = f + (size_t)(S->nrows + 1) * ny;
+    NNS_NCCL(N->GroupStart());
+    if (S->rank > 0) {
+        NNS_NCCL(N->Send(first, ny, kNcclFloat64, S->rank - 1, S->comm, st));
+        NNS_NCCL(N->Recv(top_halo, ny, kNcclFloat64, S->rank - 1, S->comm, st));
+    }
+    if (S->rank < S->nranks - 1) {
+        NNS_NCCL(N->Send(last, ny, kNcclFloat64, S->rank + 1, S->comm, st));
+        NNS_NCCL(N->Recv(bot_halo, ny, kNcclFloat64, S->rank + 1, S->comm, st));
+    }
+    NNS_NCCL(N->GroupEnd());
+    return NNS_OK;
+}
+
+int apply_bc_list(nns_handle *h, const SlabGeom &g, int field, double *A, cudaStream_t st) {
+    const BcList &L = h->bc[field];
+    for (int k = 0; k < L.n; ++k) {
+        const int n = (L.side[k] == NNS_SIDE_LEFT || L.side[k] == NNS_SIDE_RIGHT) ? g.ny : g.row1 - g.row0;
+        slab_bc_kernel<<<(n + 127) / 128, 128, 0, st>>>(g, A, L.side[k], L.type[k] == NNS_BC_NEUMANN, L.value[k]);
+        h->launches += 1;
+    }
+    NNS_CUDA(cudaGetLastError());
+    return NNS_OK;
+}
+
+int run_sweeps(nns_handle *h, SlabState *S, const SlabGeom &g, double *p, int cap, bool track, cudaStream_t st) {
+    SweepArgs a{};
+    a.g = g; a.TR = S->TR; a.nJ = S->nJ; a.I0 = S->I0; a.I1 = S->I1; a.cap = cap;
+    a.p = p; a.cp = S->d_cprime; a.flags = track ? S->d_flags : nullptr;
+    const int ntl = std::min(S->I1 - S->I0, S->nJ);
+    const dim3 grid((ntl + 3) / 4, cap);
+    const int Tmax = (S->nI - 1) + (S->nJ - 1) + 2 * (cap - 1);
+    int rc;
+    for (int T = 0; T <= Tmax; ++T) {
+        // this rank has tiles on the hyperplane iff some sweep's diagonal crosses its tile rows
+        const int dmin = T - 2 * (cap - 1), dmax = T;
+        const bool any = dmax >= S->I0 && dmin <= (S->I1 - 1) + (S->nJ - 1);
+        if (any && S->I1 > S->I0) {
+            slab_sweep_kernel<<<grid, 128, 0, st>>>(a, T);
+            h->launches += 1;
+        }
+        if ((rc = exchange_rows(h, S, p, st))) return rc;
+    }
+    NNS_CUDA(cudaGetLastError());
+    return NNS_OK;
+}
+
+}  // namespace
+
+// ---- host-side plan (pure host logic, exported through the C ABI and unit-tested on the CPU) ----------
+int slab_partition(int nx, int nranks, int rank, int tile_rows, int *row0, int *nrows, int *I0, int *I1, int *nI) {
+    if (nx < 3 || nranks < 1 || rank < 0 || rank >= nranks) { set_error("slab partition: bad argument"); return NNS_ERR_INVALID; }
+    const int TR = tile_rows > 0 ? tile_rows : tile_rows_for(nx);
+    const int n_tiles = (nx - 2 + TR - 1) / TR;
+    if (n_tiles < nranks) {
+        set_error("slab partition: %d interior rows give %d tile rows of %d, fewer than %d ranks", nx - 2, n_tiles, TR, nranks);
+        return NNS_ERR_INVALID;
+    }
+    const int a = (int)((long long)n_tiles * rank / nranks), b = (int)((long long)n_tiles * (rank + 1) / nranks);
+    const int r0 = rank == 0 ? 0 : 1 + a * TR;
+    const int r1 = rank == nranks - 1 ? nx : std::min(1 + b * TR, nx - 1);
+    if (row0) *row0 = r0;
+    if (nrows) *nrows = r1 - r0;
+    if (I0) *I0 = a;
+    if (I1) *I1 = b;
+    if (nI) *nI = n_tiles;
+    return NNS_OK;
+}
+
+// plan query: tile geometry and, per (tick, sweep), the tile rows of a rank (host logic of the tick loop)
+int slab_plan(int nx, int ny, int nranks, int rank, int tile_rows, int T, int s, int *out) {
+    int row0, nrows, I0, I1, nI, rc;
+    if ((rc = slab_partition(nx, nranks, rank, tile_rows, &row0, &nrows, &I0, &I1, &nI))) return rc;
+    const int TR = tile_rows > 0 ? tile_rows : tile_rows_for(nx);
+    const int nJ = (ny - 2 + TC - 1) / TC;
+    int Ilo = 0, Ihi = -1;
+    const bool any = tick_tile_rows(T, s, I0, I1, nJ, &Ilo, &Ihi);
+    out[0] = TR; out[1] = TC; out[2] = nI; out[3] = nJ; out[4] = I0; out[5] = I1; out[6] = any ? Ilo : 0; out[7] = any ? Ihi : -1;
+    return NNS_OK;
+}
+
+int slab_apply_bc(nns_handle *h, int field, double *a, cudaStream_t st) {
+    SlabState *S = static_cast<SlabState *>(h->slab);
+    if (!S) { set_error("slab path: call nns_slab_attach first"); return NNS_ERR_INVALID; }
+    const Geometry &G = h->g;
+    SlabGeom g{};
+    g.nx = G.nx; g.ny = G.ny; g.row0 = S->row0; g.row1 = S->row0 + S->nrows;
+    g.v.rowbase = S->row0 - 1; g.v.ny = G.ny;
+    g.dt = G.dt; g.dx = G.dx; g.dy = G.dy; g.rho = G.rho; g.nu = G.nu; g.beta = G.beta; g.tol = G.tol;
+    return apply_bc_list(h, g, field, a, st);
+}
+
+void slab_free(nns_handle *h) {
+    SlabState *S = static_cast<SlabState *>(h->slab);
+    if (!S) return;
+    if (S->comm && nccl_api()) nccl_api()->CommDestroy(S->comm);
+    cudaFree(S->d_cprime); cudaFree(S->d_p0); cudaFree(S->d_flags);
+    for (double *d : S->d_own) cudaFree(d);
+    if (S->h_flags) cudaFreeHost(S->h_flags);
+    delete S;
+    h->slab = nullptr;
+}
+
+int slab_unique_id(unsigned char *id128) {
+    NcclApi *N = nccl_api();
+    if (!N) return NNS_ERR_CUDA;
+    NcclId id;
+    NNS_NCCL(N->GetUniqueId(&id));
+    memcpy(id128, id.internal, 128);
+    return NNS_OK;
+}
+
+int slab_attach(nns_handle *h, int rank, int nranks, const unsigned char *id128) {
+    if (h->g.batch != 1 || h->g.method != NNS_METHOD_EXPLICIT) {
+        set_error("slab path: batch must be 1 and method explicit");
+        return NNS_ERR_UNSUPPORTED;
+    }
+    slab_free(h);
+    SlabState *S = new SlabState();
+    h->slab = S;
+    S->rank = rank; S->nranks = nranks;
+    S->TR = tile_rows_for(h->g.nx);
+    int rc;
+    if ((rc = slab_partition(h->g.nx, nranks, rank, S->TR, &S->row0, &S->nrows, &S->I0, &S->I1, &S->nI))) return rc;
+    S->nJ = (h->g.ny - 2 + TC - 1) / TC;
+    if (nranks > 1) {
+        NcclApi *N = nccl_api();
+        if (!N) return NNS_ERR_CUDA;
+        if (!id128) { set_error("slab attach: NCCL id missing"); return NNS_ERR_INVALID; }
+        NcclId id;
+        memcpy(id.internal, id128, 128);
+        NNS_NCCL(N->CommInitRank(&S->comm, nranks, id, rank));
+    }
+    const size_t bytes = sizeof(double) * (size_t)(S->nrows + 2) * h->g.ny;
+    NNS_CUDA(cudaMalloc(&S->d_cprime, bytes));
+    NNS_CUDA(cudaMalloc(&S->d_p0, bytes));
+    NNS_CUDA(cudaMemset(S->d_cprime, 0, bytes));
+    NNS_CUDA(cudaMalloc(&S->d_flags, sizeof(int) * 64));
+    NNS_CUDA(cudaMallocHost(&S->h_flags, sizeof(int) * 64));
+    return NNS_OK;
+}
+
+int slab_exchange(nns_handle *h, double *f, cudaStream_t st) {
+    SlabState *S = static_cast<SlabState *>(h->slab);
+    if (!S) { set_error("slab path: call nns_slab_attach first"); return NNS_ERR_INVALID; }
+    return exchange_rows(h, S, f, st);
+}
+
+// One time step on the local slabs ([nrows + 2][ny] each, halo rows valid on entry for u, v, u1, v1, p;
+// valid on return for u_out, v_out, p).  Synchronises the stream once (exit-test decision).
+int slab_step(nns_handle *h, const double *u, const double *v, const double *u1, const double *v1, double *p,
+              double *un, double *vn, int32_t *sweeps_host, cudaStream_t st) {
+    SlabState *S = static_cast<SlabState *>(h->slab);
+    if (!S) { set_error("slab path: call nns_slab_attach first"); return NNS_ERR_INVALID; }
+    const Geometry &G = h->g;
+    if (G.nit - 1 > 64) { set_error("slab path: nit <= 65"); return NNS_ERR_UNSUPPORTED; }
+    SlabGeom g{};
+    g.nx = G.nx; g.ny = G.ny; g.row0 = S->row0; g.row1 = S->row0 + S->nrows;
+    g.v.rowbase = S->row0 - 1; g.v.ny = G.ny;
+    g.dt = G.dt; g.dx = G.dx; g.dy = G.dy; g.rho = G.rho; g.nu = G.nu; g.beta = G.beta; g.tol = G.tol;
+    const dim3 blk(128), grd((G.ny + 127) / 128, S->nrows);
+    const size_t bytes = sizeof(double) * (size_t)(S->nrows + 2) * G.ny;
+    int rc;
+    slab_predictor_kernel<<<grd, blk, 0, st>>>(g, u, v, u1, v1, un, vn);
+    h->launches += 1;
+    if ((rc = apply_bc_list(h, g, 0, un, st)) || (rc = apply_bc_list(h, g, 1, vn, st))) return rc;
+    if ((rc = exchange_rows(h, S, un, st))) return rc;             // C' needs ui of the row above
+    slab_cprime_kernel<<<grd, blk, 0, st>>>(g, un, vn, S->d_cprime);
+    h->launches += 1;
+    const int cap = G.nit - 1;
+    int need = 0;
+    if (cap > 0) {
+        NNS_CUDA(cudaMemcpyAsync(S->d_p0, p, bytes, cudaMemcpyDeviceToDevice, st));
+        NNS_CUDA(cudaMemsetAsync(S->d_flags, 0, sizeof(int) * 64, st));
+        if ((rc = run_sweeps(h, S, g, p, cap, true, st))) return rc;
+        if (S->nranks > 1)
+            NNS_NCCL(nccl_api()->AllReduce(S->d_flags, S->d_flags, 64, kNcclInt32, kNcclMax, S->comm, st));
+        NNS_CUDA(cudaMemcpyAsync(S->h_flags, S->d_flags, sizeof(int) * 64, cudaMemcpyDeviceToHost, st));
+        NNS_CUDA(cudaStreamSynchronize(st));
+        need = cap;
+        for (int s = 0; s < cap; ++s)
+            if (!S->h_flags[s]) { need = s + 1; break; }      // first sweep with max|dp| <= tol: s + 1 sweeps run
+        if (need < cap) {
+            // the sequential loop would have stopped after `need` sweeps: redo from the saved p, capped
+            NNS_CUDA(cudaMemcpyAsync(p, S->d_p0, bytes, cudaMemcpyDeviceToDevice, st));
+            if ((rc = run_sweeps(h, S, g, p, need, false, st))) return rc;
+        }
+    }
+    if (sweeps_host) *sweeps_host = need;
+    if ((rc = apply_bc_list(h, g, 2, p, st))) return rc;
+    if ((rc = exchange_rows(h, S, p, st))) return rc;
+    slab_project_kernel<<<grd, blk, 0, st>>>(g, p, un, vn, h->d_nonfinite, h->params.flags & NNS_FLAG_CHECK_FINITE);
+    h->launches += 1;
+    if ((rc = exchange_rows(h, S, un, st)) || (rc = exchange_rows(h, S, vn, st))) return rc;
+    NNS_CUDA(cudaGetLastError());
+    return NNS_OK;
+}
+
+// Single-GPU run() for grids that do not fit the on-chip paths: plain [nx][ny] buffers from the caller are
+// copied into haloed slabs owned by the handle (nranks = 1), stepped, and copied back.
+int chorin_tiled_run(nns_handle *h, double *bufU[3], double *bufV[3], double *p, int nsteps, int nsteps_total,
+                     int step0, int phases, int fixup, double *tu, double *tv, double *tp, int32_t *sweeps,
+                     cudaStream_t st, int m0, int count) {
+    (void)m0; (void)count; (void)fixup;
+    if (h->g.batch != 1 || h->g.method != NNS_METHOD_EXPLICIT || phases != 7) {
+        set_error("chorin_fd: grid %dx%d does not fit the on-chip path; the tiled path supports batch 1, explicit, "
+                  "whole steps", h->g.nx, h->g.ny);
+        return NNS_ERR_UNSUPPORTED;
+    }
+    int rc;
+    if (!h->slab && (rc = slab_attach(h, 0, 1, nullptr))) return rc;
+    SlabState *S = static_cast<SlabState *>(h->slab);
+    if (S->nranks != 1) { set_error("chorin_fd: handle is attached to a multi-rank slab; use nns_chorin_fd_slab_step"); return NNS_ERR_INVALID; }
+    const size_t N = (size_t)h->g.nx * h->g.ny, nb = sizeof(double) * N, hb = sizeof(double) * (N + 2 * h->g.ny);
+    for (int k = 0; k < 7; ++k)
+        if (!S->d_own[k]) { NNS_CUDA(cudaMalloc(&S->d_own[k], hb)); NNS_CUDA(cudaMemsetAsync(S->d_own[k], 0, hb, st)); }
+    double *U[3] = {S->d_own[0], S->d_own[1], S->d_own[2]}, *V[3] = {S->d_own[3], S->d_own[4], S->d_own[5]}, *Ps = S->d_own[6];
+    const int ny = h->g.ny;
+    for (int k = 0; k < 2; ++k) {
+        NNS_CUDA(cudaMemcpyAsync(U[k] + ny, bufU[k], nb, cudaMemcpyDeviceToDevice, st));
+        NNS_CUDA(cudaMemcpyAsync(V[k] + ny, bufV[k], nb, cudaMemcpyDeviceToDevice, st));
+    }
+    NNS_CUDA(cudaMemcpyAsync(Ps + ny, p, nb, cudaMemcpyDeviceToDevice, st));
+    int cur = 0, prev = 1, nxt = 2;
+    for (int n = 0; n < nsteps; ++n) {
+        int32_t need = 0;
+        if ((rc = slab_step(h, U[cur], V[cur], U[prev], V[prev], Ps, U[nxt], V[nxt], &need, st))) return rc;
+        if (sweeps) NNS_CUDA(cudaMemcpyAsync(sweeps + (size_t)(step0 + n) * h->g.batch, &need, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        if (tu) {
+            const size_t off = (size_t)(step0 + n) * N;
+            NNS_CUDA(cudaMemcpyAsync(tu + off, U[nxt] + ny, nb, cudaMemcpyDeviceToDevice, st));
+            NNS_CUDA(cudaMemcpyAsync(tv + off, V[nxt] + ny, nb, cudaMemcpyDeviceToDevice, st));
+            NNS_CUDA(cudaMemcpyAsync(tp + off, Ps + ny, nb, cudaMemcpyDeviceToDevice, st));
+        }
+        NNS_CUDA(cudaStreamSynchronize(st));      // `need` is a host temporary
+        const int t = prev; prev = cur; cur = nxt; nxt = t;
+    }
+    (void)nsteps_total;
+    // results back into the caller's buffers with the roles the caller expects
+    if (fixup) {
+        NNS_CUDA(cudaMemcpyAsync(bufU[0], U[cur] + ny, nb, cudaMemcpyDeviceToDevice, st));
+        NNS_CUDA(cudaMemcpyAsync(bufV[0], V[cur] + ny, nb, cudaMemcpyDeviceToDevice, st));
+        NNS_CUDA(cudaMemcpyAsync(bufU[1], U[prev] + ny, nb, cudaMemcpyDeviceToDevice, st));
+        NNS_CUDA(cudaMemcpyAsync(bufV[1], V[prev] + ny, nb, cudaMemcpyDeviceToDevice, st));
+    } else {                                       // single step: new state into buffer 2
+        NNS_CUDA(cudaMemcpyAsync(bufU[2], U[cur] + ny, nb, cudaMemcpyDeviceToDevice, st));
+        NNS_CUDA(cudaMemcpyAsync(bufV[2], V[cur] + ny, nb, cudaMemcpyDeviceToDevice, st));
+    }
+    NNS_CUDA(cudaMemcpyAsync(p, Ps + ny, nb, cudaMemcpyDeviceToDevice, st));
+    return NNS_OK;
+}
+
+}  // namespace nns

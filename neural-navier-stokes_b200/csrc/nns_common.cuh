@@ -42,6 +42,7 @@ struct nns_handle {
     void *d_blockdesc;
     double *d_cprime;         // SOR right-hand side when it does not fit in shared memory
     void *stream_plan;        // chorin_fd persistent stream path: block tables + C' images
+    void *slab;               // chorin_fd tiled / row-slab path: SlabState (partition, NCCL communicator, scratch)
     void *spectral;           // chorin_spectral: SpectralPlan (operators + workspace)
     double *d_b;              // direct_fd rhs / second p buffer
     double *d_p2;
