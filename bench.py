@@ -35,6 +35,12 @@ WORKLOADS = {
     "ensemble4096_cavity128": (128, 128, 4096, 50, 2e-4),
     "ensemble_cavity41": (41, 41, 8192, 50, 1e-3),
 }
+# one large grid split into row slabs over the GPUs (BASELINE configs[4]): name -> (nx, ny, nit, dt, nu)
+SLAB_WORKLOADS = {
+    "slab_cavity16384": (16384, 16384, 50, 1e-8, 0.1),
+    "slab_cavity4096": (4096, 4096, 50, 1.5e-7, 0.1),
+}
+BYTES_PER_CELL_SWEEP = 24       # read p, read C', write p in an un-blocked sweep
 
 
 def peaks():
@@ -170,13 +176,81 @@ def run_reference(args, rank, world):
         "gpu_launches": 0}))
 
 
+def run_slab(args, rank, world, local):
+    """One large chorin_fd grid on row slabs (strong scaling): a step = one time step of the whole grid."""
+    import torch
+    import torch.distributed as dist
+    from nns_b200.ensemble import cavity_bcs
+    from nns_b200.slab import SlabChorin
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nx, ny, nit, dt, nu = SLAB_WORKLOADS[args.workload]
+    dx, dy = 2. / (nx - 1), 2. / (ny - 1)
+    u_bc, v_bc, p_bc = cavity_bcs(dx, dy)
+    sl = SlabChorin(nx, ny, u_bc=u_bc, v_bc=v_bc, p_bc=p_bc, nit=nit, dt=dt, rho=1, nu=nu, beta=1.25)
+    sl.init_variables()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        sl.step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = sl.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sor_ms, sweeps = [], []
+    for _ in range(args.steps):
+        sl.step()
+        ms, ticks = sl.last_sor_timing()
+        sor_ms.append(ms)
+        sweeps.append(sl.last_sweeps)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    finite = bool(torch.isfinite(sl.u).all() and torch.isfinite(sl.p).all())
+    if rank == 0:
+        peak, peak_src = peaks()
+        cells = nx * ny
+        kms = float(np.mean(sor_ms)) / ticks          # average sweep-kernel launch (one tick), exchange included for N > 1
+        S = float(np.mean(sweeps))
+        achieved = BYTES_PER_CELL_SWEEP * (cells / world) * S / ticks / (kms * 1e-3) / 1e9
+        print(json.dumps({
+            "metric": METRIC, "value": cells * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "nx": nx, "ny": ny, "nit": nit, "dt": dt, "nu": nu, "beta": 1.25,
+                       "method": "explicit", "parallelism": "row slabs, NCCL send/recv of halo rows per SOR tick",
+                       "l2": "p + C' per GPU %.2f GB >> 126 MB L2" % (2 * cells * 8 / world / 1e9),
+                       "sweeps_per_step": [int(min(sweeps)), int(max(sweeps))], "ticks_per_step": int(ticks),
+                       "finite": finite},
+            "e2e": None, "gpu_launches": int(sl.launches - l0), "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "slab_sweep_kernel",
+                         "bytes_per_cell_sweep": BYTES_PER_CELL_SWEEP, "kernel_ms": kms,
+                         "note": "un-blocked exact-order sweeps: 24 B per cell and sweep; per-tick launch average over "
+                                 "the tick loop of a step (CUDA events inside the library)"}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="ensemble4096_cavity128", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="ensemble4096_cavity128", choices=sorted(WORKLOADS) + sorted(SLAB_WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--members", type=int, default=None, help="override members per GPU")
@@ -186,6 +260,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload in SLAB_WORKLOADS:
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "slab workloads have no CPU arm; use the default workload"}))
+            return
+        run_slab(args, rank, world, local)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

@@ -196,7 +196,8 @@ int32_t nns_slab_partition(int32_t nx, int32_t nranks, int32_t rank, int32_t til
                            int32_t *nrows);
 /* Tick plan (pure host logic): out8 = {tile rows TR, tile columns TC, nI, nJ, I0, I1, Ilo, Ihi}: the tile grid, the
  * tile rows [I0, I1) of `rank`, and the tile rows [Ilo, Ihi] it sweeps at (tick, sweep) -- empty if Ihi < Ilo.
- * Tile (I, J) performs sweep s at tick I + J + 2s; J = tick - 2*sweep - I. */
+ * Tile (I, J) = rows [1 + I*TR, 1 + (I+1)*TR) x columns [J*TC, (J+1)*TC) of the interior performs sweep s at tick
+ * I + J + 2s; J = tick - 2*sweep - I. */
 int32_t nns_slab_plan(int32_t nx, int32_t ny, int32_t nranks, int32_t rank, int32_t tile_rows, int32_t tick,
                       int32_t sweep, int32_t *out8);
 /* The BC list of `field` in list order on a local slab (src/boundary.py:34-86; _init_variables :236-249). */
@@ -212,6 +213,8 @@ int32_t nns_slab_exchange(nns_handle *h, double *field, void *stream);
  * sweeps_out_host: host int32 or NULL.  The call synchronises the stream once (exit-test decision). */
 int32_t nns_chorin_fd_slab_step(nns_handle *h, const double *u, const double *v, const double *u1, const double *v1,
                                 double *p, double *u_out, double *v_out, int32_t *sweeps_out_host, void *stream);
+/* Device time (CUDA events) of the SOR tick loop of the last step and its number of ticks (= sweep-kernel launches). */
+int32_t nns_slab_last_timing(nns_handle *h, float *sor_ms, int32_t *ticks);
 
 #ifdef __cplusplus
 }

@@ -44,6 +44,7 @@ int slab_apply_bc(nns_handle *h, int field, double *a, cudaStream_t st);
 int slab_unique_id(unsigned char *id128);
 int slab_attach(nns_handle *h, int rank, int nranks, const unsigned char *id128);
 int slab_exchange(nns_handle *h, double *f, cudaStream_t st);
+int slab_last_timing(nns_handle *h, float *sor_ms, int *ticks);
 int slab_step(nns_handle *h, const double *u, const double *v, const double *u1, const double *v1, double *p,
               double *un, double *vn, int32_t *sweeps_host, cudaStream_t st);
 // direct_fd.cu
@@ -543,6 +544,12 @@ int32_t nns_slab_exchange(nns_handle *h, double *field, void *stream) {
     NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_FD);
     if (!field) { set_error("nns_slab_exchange: null field"); return NNS_ERR_INVALID; }
     return slab_exchange(h, field, (cudaStream_t)stream);
+}
+
+int32_t nns_slab_last_timing(nns_handle *h, float *sor_ms, int32_t *ticks) {
+    NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_FD);
+    if (!sor_ms || !ticks) { set_error("nns_slab_last_timing: null argument"); return NNS_ERR_INVALID; }
+    return slab_last_timing(h, sor_ms, ticks);
 }
 
 int32_t nns_chorin_fd_slab_step(nns_handle *h, const double *u, const double *v, const double *u1, const double *v1,

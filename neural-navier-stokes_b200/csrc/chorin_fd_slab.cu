@@ -90,6 +90,8 @@ struct SlabState {
     double *d_own[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // single-GPU run(): haloed copies
     int *d_flags = nullptr;       // [64] per-sweep "not converged" flags
     int *h_flags = nullptr;       // pinned
+    cudaEvent_t ev[2] = {nullptr, nullptr};   // around the tick loop of the last step
+    int last_ticks = 0;
 };
 
 struct SlabView {                 // addressing of the local slab of a field: element (i, j) of the GLOBAL grid
@@ -211,7 +213,35 @@ struct SweepArgs {
     int *flags;        // [cap] set to 1 when sweep s still violates the exit test; null = no tracking
 };
 
+// 4 consecutive doubles of a row: one 256-bit access when the address is 32-byte aligned (VEC), else scalars
+template <bool VEC>
+__device__ __forceinline__ void load4(const double *p, int nvalid, double (&x)[LC]) {
+    if (VEC) {
+        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(x[3]) : "l"(p));
+    } else {
+#pragma unroll
+        for (int jj = 0; jj < LC; ++jj) x[jj] = jj < nvalid ? p[jj] : 0.0;
+    }
+}
+template <bool VEC>
+__device__ __forceinline__ void store4(double *p, int nvalid, const double (&x)[LC]) {
+    if (VEC) {
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]) : "memory");
+    } else {
+#pragma unroll
+        for (int jj = 0; jj < LC; ++jj)
+            if (jj < nvalid) p[jj] = x[jj];
+    }
+}
+
 // All tiles of hyperplane T (see the header).  blockIdx.y = sweep, 4 warps per CTA = 4 tiles.
+// Tile J covers the global columns [J*TC, (J+1)*TC): lane chunks start on multiples of 4, so with ny % 4 == 0
+// every row chunk is ONE 256-bit load / store (LDG.E.ENL2.256).  That matters: the lanes of a warp work on 32
+// different rows, every access of the warp touches 32 cache lines, and the kernel is bound by the number of
+// load / store INSTRUCTIONS (one LSU cycle per line), not by bytes.  Per step and lane: one load of the row
+// below, one of C', one store; the east operand comes from lane + 1 by shuffle (it holds that value as its own
+// south / first row), the west one from lane - 1 (freshly updated).
+template <bool VEC>
 __global__ void __launch_bounds__(128) slab_sweep_kernel(const SweepArgs a, int T) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s = blockIdx.y;
@@ -224,51 +254,90 @@ __global__ void __launch_bounds__(128) slab_sweep_kernel(const SweepArgs a, int 
     const int ny = g.ny;
     const int i0 = 1 + I * a.TR, i1 = min(i0 + a.TR, g.nx - 1);
     const int nr = i1 - i0;
-    const int c0 = 1 + J * TC + lane * LC;
-    const int nc = max(0, min(LC, ny - 1 - c0));         // valid columns of this lane
+    const int c0 = J * TC + lane * LC;                    // first column of the lane's chunk (multiple of 4)
+    const int nin = max(0, min(LC, ny - c0));             // columns of the chunk inside the grid
+    const bool has = nin > 0 && c0 < ny - 1;              // the chunk holds at least one interior column
+    bool ok[LC];                                          // interior (updated) cells of the chunk
+#pragma unroll
+    for (int jj = 0; jj < LC; ++jj) ok[jj] = c0 + jj >= 1 && c0 + jj <= ny - 2;
+    const bool east_load = has && (lane == 31 || c0 + LC >= ny - 1) && c0 + LC <= ny - 1;   // no lane + 1 to ask
     const double dx2 = g.dx * g.dx, dy2 = g.dy * g.dy, den = 2.0 * dx2 + 2.0 * dy2;
     const double ca = g.beta * dy2 / den, cb = g.beta * dx2 / den, mbeta = -g.beta, tol = g.tol;
     double *P = a.p;
     const double *CP = a.cp;
 
-    double pn[LC], pc[LC], ps[LC];
-    double wlast = 0.0;            // the lane's last updated value of the current row (west operand of lane + 1)
+    // Software pipeline: the operands of row k are loaded PF steps before they are used, into a register ring
+    // indexed by the step number (tau mod PF is the same for the load and the use of a row on every lane).
+#ifndef NNS_SLAB_PF
+#define NNS_SLAB_PF 4
+#endif
+    constexpr int PF = NNS_SLAB_PF;
+    double pn[LC], pc[LC];
+    double qs[PF][LC], qc[PF][LC], qe[PF], qw[PF];
+    double wlast = 0.0;            // the lane's last value of the current row (west operand of lane + 1)
     bool viol = false;
 #pragma unroll
-    for (int jj = 0; jj < LC; ++jj) { pn[jj] = 0.0; pc[jj] = 0.0; ps[jj] = 0.0; }
-    for (int tau = 0; tau < nr + 31; ++tau) {
-        const int k = tau - lane;
-        const bool act = nc > 0 && k >= 0 && k < nr;
-        const int i = i0 + k;
-        const double wsh = __shfl_up_sync(0xffffffffu, wlast, 1);      // lane - 1 finished row k one step ago
-        if (act) {
-            const size_t q = g.v.at(i, c0);
-            if (k == 0) {
+    for (int jj = 0; jj < LC; ++jj) { pn[jj] = 0.0; pc[jj] = 0.0; }
 #pragma unroll
-                for (int jj = 0; jj < LC; ++jj)
-                    if (jj < nc) { pn[jj] = P[q - ny + jj]; pc[jj] = P[q + jj]; }
-            }
-            double cpv[LC];
+    for (int dd = 0; dd < PF; ++dd) {
+        qe[dd] = 0.0; qw[dd] = 0.0;
 #pragma unroll
-            for (int jj = 0; jj < LC; ++jj)
-                if (jj < nc) { ps[jj] = P[q + ny + jj]; cpv[jj] = CP[q + jj]; }
-            const double east = P[q + nc];
-            double w = lane == 0 ? P[q - 1] : wsh;
-#pragma unroll
-            for (int jj = 0; jj < LC; ++jj)
-                if (jj < nc) {
-                    const double e = (jj + 1 < nc) ? pc[jj + 1] : east;
-                    const double z = fma(ca, ps[jj], fma(cb, e, fma(mbeta, pc[jj], -cpv[jj])));
-                    const double dd = fma(ca, pn[jj], fma(cb, w, z));
-                    viol |= !(fabs(dd) <= tol);
-                    w = pc[jj] + dd;
-                    P[q + jj] = w;
-                    pn[jj] = w;
-                    pc[jj] = ps[jj];
-                }
-            wlast = w;
+        for (int jj = 0; jj < LC; ++jj) { qs[dd][jj] = 0.0; qc[dd][jj] = 0.0; }
+    }
+    auto prefetch = [&](int k, int slot) {        // operands of tile row k into ring slot `slot`
+        if (has && k >= 0 && k < nr) {
+            const size_t q = g.v.at(i0 + k, c0);
+            load4<VEC>(P + q + ny, nin, qs[slot]);
+            load4<VEC>(CP + q, nin, qc[slot]);
+            if (east_load) qe[slot] = P[q + LC];
+            if (lane == 0 && c0 > 0) qw[slot] = P[q - 1];
         }
-        __syncwarp();
+    };
+    // the lane's first row and the row above it, once, before the pipeline starts (a load inside the step loop
+    // would stall the WHOLE warp at the next use of pc / pn: the scoreboard tracks registers per warp)
+    if (has) {
+        const size_t q = g.v.at(i0, c0);
+        load4<VEC>(P + q - ny, nin, pn);
+        load4<VEC>(P + q, nin, pc);
+    }
+#pragma unroll
+    for (int dd = 0; dd < PF; ++dd) prefetch(dd - lane, dd);        // steps tau = 0 .. PF-1 use slots 0 .. PF-1
+    for (int tau0 = 0; tau0 < nr + 31; tau0 += PF) {
+#pragma unroll
+        for (int dd = 0; dd < PF; ++dd) {
+            const int tau = tau0 + dd;
+            const int k = tau - lane;
+            const bool act = has && k >= 0 && k < nr;
+            // west: lane - 1 finished row k one step ago.  east: lane + 1 is one row behind and holds row k as the
+            // row below its current one (or, before its first step, as its preloaded first row).
+            const double wsh = __shfl_up_sync(0xffffffffu, wlast, 1);
+            const double esh = __shfl_down_sync(0xffffffffu, k >= 0 ? qs[dd][0] : pc[0], 1);     // evaluated by the SOURCE lane with its own k
+            if (act) {
+                const size_t q = g.v.at(i0 + k, c0);
+                double w = lane == 0 ? qw[dd] : wsh;
+                const double east = east_load ? qe[dd] : esh;
+                double out[LC];
+#pragma unroll
+                for (int jj = 0; jj < LC; ++jj) {
+                    const double e = jj + 1 < LC ? pc[jj + 1] : east;
+                    const double z = fma(ca, qs[dd][jj], fma(cb, e, fma(mbeta, pc[jj], -qc[dd][jj])));
+                    const double dd2 = fma(ca, pn[jj], fma(cb, w, z));
+                    if (ok[jj]) {
+                        viol |= !(fabs(dd2) <= tol);
+                        w = pc[jj] + dd2;
+                    } else {
+                        w = pc[jj];        // boundary column: frozen, still the west operand of the next cell
+                    }
+                    out[jj] = w;
+                    pn[jj] = w;
+                    pc[jj] = qs[dd][jj];
+                }
+                store4<VEC>(P + q, nin, out);
+                wlast = w;
+            }
+            prefetch(k + PF, dd);      // refill the slot just consumed with the row PF steps ahead
+            __syncwarp();
+        }
     }
     if (a.flags && __any_sync(0xffffffffu, viol) && lane == 0) atomicOr(&a.flags[s], 1);
 }
@@ -316,7 +385,8 @@ int run_sweeps(nns_handle *h, SlabState *S, const SlabGeom &g, double *p, int ca
         const int dmin = T - 2 * (cap - 1), dmax = T;
         const bool any = dmax >= S->I0 && dmin <= (S->I1 - 1) + (S->nJ - 1);
         if (any && S->I1 > S->I0) {
-            slab_sweep_kernel<<<grid, 128, 0, st>>>(a, T);
+            if (g.ny % 4 == 0) slab_sweep_kernel<true><<<grid, 128, 0, st>>>(a, T);
+            else slab_sweep_kernel<false><<<grid, 128, 0, st>>>(a, T);
             h->launches += 1;
         }
         if ((rc = exchange_rows(h, S, p, st))) return rc;
@@ -352,7 +422,7 @@ int slab_plan(int nx, int ny, int nranks, int rank, int tile_rows, int T, int s,
     int row0, nrows, I0, I1, nI, rc;
     if ((rc = slab_partition(nx, nranks, rank, tile_rows, &row0, &nrows, &I0, &I1, &nI))) return rc;
     const int TR = tile_rows > 0 ? tile_rows : tile_rows_for(nx);
-    const int nJ = (ny - 2 + TC - 1) / TC;
+    const int nJ = (ny - 1 + TC - 1) / TC;
     int Ilo = 0, Ihi = -1;
     const bool any = tick_tile_rows(T, s, I0, I1, nJ, &Ilo, &Ihi);
     out[0] = TR; out[1] = TC; out[2] = nI; out[3] = nJ; out[4] = I0; out[5] = I1; out[6] = any ? Ilo : 0; out[7] = any ? Ihi : -1;
@@ -377,6 +447,8 @@ void slab_free(nns_handle *h) {
     cudaFree(S->d_cprime); cudaFree(S->d_p0); cudaFree(S->d_flags);
     for (double *d : S->d_own) cudaFree(d);
     if (S->h_flags) cudaFreeHost(S->h_flags);
+    if (S->ev[0]) cudaEventDestroy(S->ev[0]);
+    if (S->ev[1]) cudaEventDestroy(S->ev[1]);
     delete S;
     h->slab = nullptr;
 }
@@ -402,7 +474,7 @@ int slab_attach(nns_handle *h, int rank, int nranks, const unsigned char *id128)
     S->TR = tile_rows_for(h->g.nx);
     int rc;
     if ((rc = slab_partition(h->g.nx, nranks, rank, S->TR, &S->row0, &S->nrows, &S->I0, &S->I1, &S->nI))) return rc;
-    S->nJ = (h->g.ny - 2 + TC - 1) / TC;
+    S->nJ = (h->g.ny - 1 + TC - 1) / TC;     // tile J covers the columns [J*TC, (J+1)*TC) up to ny-2
     if (nranks > 1) {
         NcclApi *N = nccl_api();
         if (!N) return NNS_ERR_CUDA;
@@ -417,6 +489,18 @@ int slab_attach(nns_handle *h, int rank, int nranks, const unsigned char *id128)
     NNS_CUDA(cudaMemset(S->d_cprime, 0, bytes));
     NNS_CUDA(cudaMalloc(&S->d_flags, sizeof(int) * 64));
     NNS_CUDA(cudaMallocHost(&S->h_flags, sizeof(int) * 64));
+    NNS_CUDA(cudaEventCreate(&S->ev[0]));
+    NNS_CUDA(cudaEventCreate(&S->ev[1]));
+    return NNS_OK;
+}
+
+// device time of the tick loop (tracked sweeps) of the last step and its number of ticks (bench.py's roofline)
+int slab_last_timing(nns_handle *h, float *sor_ms, int *ticks) {
+    SlabState *S = static_cast<SlabState *>(h->slab);
+    if (!S || !S->last_ticks) { set_error("slab path: no step has run"); return NNS_ERR_INVALID; }
+    NNS_CUDA(cudaEventSynchronize(S->ev[1]));
+    NNS_CUDA(cudaEventElapsedTime(sor_ms, S->ev[0], S->ev[1]));
+    *ticks = S->last_ticks;
     return NNS_OK;
 }
 
@@ -452,7 +536,10 @@ int slab_step(nns_handle *h, const double *u, const double *v, const double *u1,
     if (cap > 0) {
         NNS_CUDA(cudaMemcpyAsync(S->d_p0, p, bytes, cudaMemcpyDeviceToDevice, st));
         NNS_CUDA(cudaMemsetAsync(S->d_flags, 0, sizeof(int) * 64, st));
+        NNS_CUDA(cudaEventRecord(S->ev[0], st));
         if ((rc = run_sweeps(h, S, g, p, cap, true, st))) return rc;
+        NNS_CUDA(cudaEventRecord(S->ev[1], st));
+        S->last_ticks = (S->nI - 1) + (S->nJ - 1) + 2 * (cap - 1) + 1;
         if (S->nranks > 1)
             NNS_NCCL(nccl_api()->AllReduce(S->d_flags, S->d_flags, 64, kNcclInt32, kNcclMax, S->comm, st));
         NNS_CUDA(cudaMemcpyAsync(S->h_flags, S->d_flags, sizeof(int) * 64, cudaMemcpyDeviceToHost, st));

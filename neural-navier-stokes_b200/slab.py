@@ -105,6 +105,12 @@ class SlabChorin:
             out[r0:r0 + a.shape[0]] = a
         return out
 
+    def last_sor_timing(self):
+        """(ms, ticks) of the SOR tick loop of the last step (device time)."""
+        ms, tk = C.c_float(0), C.c_int32(0)
+        _lib.check(self._L.nns_slab_last_timing(self.handle.h, C.byref(ms), C.byref(tk)))
+        return ms.value, tk.value
+
     @property
     def launches(self):
         return self.handle.launches

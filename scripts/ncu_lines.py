@@ -26,7 +26,7 @@ for l in sorted(lines, key=lambda x: -x[3])[:top]:
 if len(sys.argv) > 3:      # extra args: name:lo-hi line ranges of the main file to aggregate
     for spec in sys.argv[3:]:
         name, rng = spec.split(':'); lo, hi = map(int, rng.split('-'))
-        sel = [l for l in lines if lo <= l[1] <= hi and l[0].startswith('chorin_fd_stre')]
+        sel = [l for l in lines if lo <= l[1] <= hi and l[0].startswith('chorin_fd_slab')]
         tots = sum(l[3] for l in sel)
         agg = {}
         for l in sel:

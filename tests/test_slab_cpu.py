@@ -97,7 +97,7 @@ def _slab_worker(rank, world, port, nx, ny, tr, cap, q):
             for I in range(pl["Ilo"], pl["Ihi"] + 1):
                 J = T - 2 * s - I
                 for i in range(1 + I * TR, min(1 + (I + 1) * TR, nx - 1)):
-                    for j in range(1 + J * TC, min(1 + (J + 1) * TC, ny - 1)):
+                    for j in range(max(1, J * TC), min((J + 1) * TC, ny - 1)):
                         l = L(i)
                         p[l, j] = beta * (dy ** 2 * p[l + 1, j] + dy ** 2 * p[l - 1, j] + dx ** 2 * p[l, j + 1] +
                                           dx ** 2 * p[l, j - 1] - Cg[i, j]) / (2 * dx ** 2 + 2 * dy ** 2) + (1 - beta) * p[l, j]
