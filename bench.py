@@ -376,10 +376,11 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "chorin_chip_kernel", "bytes_per_cell_update": BYTES_PER_CELL_UPDATE,
+                         "kernel": "chorin_stream_kernel", "bytes_per_cell_update": BYTES_PER_CELL_UPDATE,
                          "kernel_ms": kms,
-                         "note": "fused step is fp64-pipe/smem bound before HBM (about 300 fp64 ops and "
-                                 "49 in-smem sweeps per 64 algorithmic bytes); see DESIGN.md"},
+                         "note": "one launch = one fused step of all members; FP64-pipe / shared-memory bound before "
+                                 "HBM (49 exact-order SOR sweeps x 6 FP64 instr per cell: FP64 floor 1.2-1.4 ms/step "
+                                 "vs HBM floor 0.66 ms); see DESIGN.md 4.1"},
         }
         prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(prof):
