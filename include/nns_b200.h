@@ -206,6 +206,12 @@ int32_t nns_slab_apply_bc(nns_handle *h, int32_t field, double *a, void *stream)
 int32_t nns_nccl_unique_id(uint8_t *id128);
 /* Attach the handle to its slab; creates the NCCL communicator when nranks > 1 (collective call). */
 int32_t nns_slab_attach(nns_handle *h, int32_t rank, int32_t nranks, const uint8_t *id128);
+/* Optional peer-memory exchange for the SOR tick loop: every rank exports the 64-byte CUDA IPC handle of its
+ * mailbox and maps the mailboxes of the ranks above / below (NULL at the ends).  Boundary rows of p then travel
+ * as NVLink stores + flags issued from the tick loop's own stream (no NCCL launch per tick), and the tile rows
+ * next to a neighbour are swept first so that the transfer hides behind the interior tile rows. */
+int32_t nns_slab_ipc_export(nns_handle *h, uint8_t *handle64);
+int32_t nns_slab_ipc_connect(nns_handle *h, const uint8_t *above64, const uint8_t *below64);
 /* Swap the boundary rows of one local field with the neighbouring ranks (fills the halo rows). */
 int32_t nns_slab_exchange(nns_handle *h, double *field, void *stream);
 /* One time step (step(), chorin_fd/simulate.py:212-234) on the local slabs.  Halo rows of u, v, u1, v1, p must be

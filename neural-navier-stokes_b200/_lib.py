@@ -57,6 +57,8 @@ _PROTOS = {
     "nns_nccl_unique_id": (_i32, [_vp]),
     "nns_slab_attach": (_i32, [_vp, _i32, _i32, _vp]),
     "nns_slab_exchange": (_i32, [_vp, _vp, _vp]),
+    "nns_slab_ipc_export": (_i32, [_vp, _vp]),
+    "nns_slab_ipc_connect": (_i32, [_vp, _vp, _vp]),
     "nns_chorin_fd_slab_step": (_i32, [_vp] * 10),
     "nns_slab_last_timing": (_i32, [_vp, C.POINTER(C.c_float), C.POINTER(_i32)]),
     "nns_spectral_set_operators": (_i32, [_vp, C.POINTER(_vp), _i32]),

@@ -45,6 +45,8 @@ int slab_unique_id(unsigned char *id128);
 int slab_attach(nns_handle *h, int rank, int nranks, const unsigned char *id128);
 int slab_exchange(nns_handle *h, double *f, cudaStream_t st);
 int slab_last_timing(nns_handle *h, float *sor_ms, int *ticks);
+int slab_ipc_export(nns_handle *h, unsigned char *handle64);
+int slab_ipc_connect(nns_handle *h, const unsigned char *above64, const unsigned char *below64);
 int slab_step(nns_handle *h, const double *u, const double *v, const double *u1, const double *v1, double *p,
               double *un, double *vn, int32_t *sweeps_host, cudaStream_t st);
 // direct_fd.cu
@@ -544,6 +546,17 @@ int32_t nns_slab_exchange(nns_handle *h, double *field, void *stream) {
     NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_FD);
     if (!field) { set_error("nns_slab_exchange: null field"); return NNS_ERR_INVALID; }
     return slab_exchange(h, field, (cudaStream_t)stream);
+}
+
+int32_t nns_slab_ipc_export(nns_handle *h, uint8_t *handle64) {
+    NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_FD);
+    if (!handle64) { set_error("nns_slab_ipc_export: null argument"); return NNS_ERR_INVALID; }
+    return slab_ipc_export(h, handle64);
+}
+
+int32_t nns_slab_ipc_connect(nns_handle *h, const uint8_t *above64, const uint8_t *below64) {
+    NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_FD);
+    return slab_ipc_connect(h, above64, below64);
 }
 
 int32_t nns_slab_last_timing(nns_handle *h, float *sor_ms, int32_t *ticks) {

@@ -21,6 +21,7 @@
 // ranks swap their boundary rows of p (the row above supplies "north, same sweep", the row below "south,
 // previous sweep").  u, v, the predictor output and the final p swap halo rows once per step.  The per-sweep
 // exit flags are max-reduced over the ranks, so every rank takes the reference's early-exit decision.
+#include <cuda.h>
 #include <dlfcn.h>
 #include <stdlib.h>
 
@@ -91,6 +92,12 @@ struct SlabState {
     int *d_flags = nullptr;       // [64] per-sweep "not converged" flags
     int *h_flags = nullptr;       // pinned
     cudaEvent_t ev[2] = {nullptr, nullptr};   // around the tick loop of the last step
+    // peer-memory halo exchange of p inside the tick loop (NVLink stores + flags instead of NCCL launches)
+    unsigned char *d_box = nullptr;           // this rank's mailbox: rows [dir][buf][ny] doubles, then flags[2] (uint32)
+    unsigned char *peer_box[2] = {nullptr, nullptr};   // mapped mailboxes of the rank above (0) / below (1)
+    bool p2p = false;
+    unsigned seq = 0;                         // tick sequence number (monotonic over the run)
+    CUresult (*StreamWaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
     int last_ticks = 0;
 };
 
@@ -372,24 +379,96 @@ int apply_bc_list(nns_handle *h, const SlabGeom &g, int field, double *A, cudaSt
     return NNS_OK;
 }
 
+// mailbox layout of a rank: rows[dir][buf][ny] doubles (dir 0: written by the rank ABOVE, its last row; dir 1:
+// written by the rank BELOW, its first row; buf = tick parity), then flags[dir] (uint32 sequence numbers)
+__host__ __device__ inline size_t box_row_off(int dir, int buf, int ny) { return sizeof(double) * (size_t)(dir * 2 + buf) * ny; }
+__host__ __device__ inline size_t box_flag_off(int dir, int ny) { return sizeof(double) * (size_t)4 * ny + sizeof(unsigned) * dir; }
+inline size_t box_bytes(int ny) { return sizeof(double) * (size_t)4 * ny + 64; }
+
+// One boundary row into the neighbour's mailbox over NVLink, then its flag (system-scope release).
+__global__ void __launch_bounds__(1024) slab_push_row_kernel(const double *__restrict__ src, double *dst, int ny,
+                                                             volatile unsigned *flag, unsigned seq) {
+    for (int j = threadIdx.x; j < ny; j += blockDim.x) dst[j] = src[j];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *flag = seq;
+}
+
+int launch_sweep(nns_handle *h, SlabState *S, SweepArgs a, int Ia, int Ib, int T, cudaStream_t st) {
+    if (Ib <= Ia) return NNS_OK;
+    const int dmin = T - 2 * (a.cap - 1), dmax = T;
+    if (!(dmax >= Ia && dmin <= (Ib - 1) + (S->nJ - 1))) return NNS_OK;     // no diagonal crosses these tile rows
+    a.I0 = Ia; a.I1 = Ib;
+    const int ntl = std::min(Ib - Ia, S->nJ);
+    const dim3 grid((ntl + 3) / 4, a.cap);
+    if (a.g.ny % 4 == 0) slab_sweep_kernel<true><<<grid, 128, 0, st>>>(a, T);
+    else slab_sweep_kernel<false><<<grid, 128, 0, st>>>(a, T);
+    h->launches += 1;
+    return NNS_OK;
+}
+
 int run_sweeps(nns_handle *h, SlabState *S, const SlabGeom &g, double *p, int cap, bool track, cudaStream_t st) {
     SweepArgs a{};
     a.g = g; a.TR = S->TR; a.nJ = S->nJ; a.I0 = S->I0; a.I1 = S->I1; a.cap = cap;
     a.p = p; a.cp = S->d_cprime; a.flags = track ? S->d_flags : nullptr;
-    const int ntl = std::min(S->I1 - S->I0, S->nJ);
-    const dim3 grid((ntl + 3) / 4, cap);
     const int Tmax = (S->nI - 1) + (S->nJ - 1) + 2 * (cap - 1);
+    const int ny = g.ny;
     int rc;
+    if (!S->p2p) {
+        for (int T = 0; T <= Tmax; ++T) {
+            if ((rc = launch_sweep(h, S, a, S->I0, S->I1, T, st))) return rc;
+            if ((rc = exchange_rows(h, S, p, st))) return rc;
+        }
+        NNS_CUDA(cudaGetLastError());
+        return NNS_OK;
+    }
+    // Peer-memory exchange.  Per tick, in stream order: (1) wait for the neighbours' rows of the previous tick
+    // (stream memory operation on this rank's mailbox flag) and copy them into the halo rows, (2) sweep the
+    // tiles of the tick, (3) push the fresh boundary rows into the neighbours' mailboxes over NVLink and raise
+    // their flags.  No NCCL kernel and no host synchronisation inside the tick loop.
+    const bool up = S->rank > 0, dn = S->rank < S->nranks - 1;
+    double *top_halo = p, *first = p + ny, *last = p + (size_t)S->nrows * ny, *bot_halo = p + (size_t)(S->nrows + 1) * ny;
     for (int T = 0; T <= Tmax; ++T) {
-        // this rank has tiles on the hyperplane iff some sweep's diagonal crosses its tile rows
-        const int dmin = T - 2 * (cap - 1), dmax = T;
-        const bool any = dmax >= S->I0 && dmin <= (S->I1 - 1) + (S->nJ - 1);
-        if (any && S->I1 > S->I0) {
-            if (g.ny % 4 == 0) slab_sweep_kernel<true><<<grid, 128, 0, st>>>(a, T);
-            else slab_sweep_kernel<false><<<grid, 128, 0, st>>>(a, T);
+        const unsigned prev = S->seq;           // sequence number of the previous tick's rows
+        const unsigned cur = ++S->seq;
+        const int rb = prev & 1, wb = cur & 1;
+        if (T > 0) {
+            if (up) {
+                if (S->StreamWaitValue32((CUstream)st, (CUdeviceptr)(S->d_box + box_flag_off(0, ny)), prev, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) { set_error("cuStreamWaitValue32 failed"); return NNS_ERR_CUDA; }
+                NNS_CUDA(cudaMemcpyAsync(top_halo, S->d_box + box_row_off(0, rb, ny), sizeof(double) * ny, cudaMemcpyDeviceToDevice, st));
+            }
+            if (dn) {
+                if (S->StreamWaitValue32((CUstream)st, (CUdeviceptr)(S->d_box + box_flag_off(1, ny)), prev, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) { set_error("cuStreamWaitValue32 failed"); return NNS_ERR_CUDA; }
+                NNS_CUDA(cudaMemcpyAsync(bot_halo, S->d_box + box_row_off(1, rb, ny), sizeof(double) * ny, cudaMemcpyDeviceToDevice, st));
+            }
+        }
+        // One launch for all tile rows of the tick (a tile-sweep is one warp walking 128 + 31 dependent steps, so a
+        // separate launch for the tile rows next to a neighbour costs a full tile latency per tick: measured
+        // slower), then the fresh boundary rows go to the neighbours' mailboxes.
+        if ((rc = launch_sweep(h, S, a, S->I0, S->I1, T, st))) return rc;
+        if (up) {       // my first row is the "south, previous sweep" operand of the rank above: its mailbox dir 1
+            slab_push_row_kernel<<<1, 1024, 0, st>>>(first, reinterpret_cast<double *>(S->peer_box[0] + box_row_off(1, wb, ny)), ny,
+                                                     reinterpret_cast<volatile unsigned *>(S->peer_box[0] + box_flag_off(1, ny)), cur);
             h->launches += 1;
         }
-        if ((rc = exchange_rows(h, S, p, st))) return rc;
+        if (dn) {       // my last row is the "north, same sweep" operand of the rank below: its mailbox dir 0
+            slab_push_row_kernel<<<1, 1024, 0, st>>>(last, reinterpret_cast<double *>(S->peer_box[1] + box_row_off(0, wb, ny)), ny,
+                                                     reinterpret_cast<volatile unsigned *>(S->peer_box[1] + box_flag_off(0, ny)), cur);
+            h->launches += 1;
+        }
+    }
+    // the halo rows of the final state (the rows pushed at the last tick)
+    {
+        const unsigned prev = S->seq;
+        const int rb = prev & 1;
+        if (up) {
+            if (S->StreamWaitValue32((CUstream)st, (CUdeviceptr)(S->d_box + box_flag_off(0, ny)), prev, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) { set_error("cuStreamWaitValue32 failed"); return NNS_ERR_CUDA; }
+            NNS_CUDA(cudaMemcpyAsync(top_halo, S->d_box + box_row_off(0, rb, ny), sizeof(double) * ny, cudaMemcpyDeviceToDevice, st));
+        }
+        if (dn) {
+            if (S->StreamWaitValue32((CUstream)st, (CUdeviceptr)(S->d_box + box_flag_off(1, ny)), prev, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) { set_error("cuStreamWaitValue32 failed"); return NNS_ERR_CUDA; }
+            NNS_CUDA(cudaMemcpyAsync(bot_halo, S->d_box + box_row_off(1, rb, ny), sizeof(double) * ny, cudaMemcpyDeviceToDevice, st));
+        }
     }
     NNS_CUDA(cudaGetLastError());
     return NNS_OK;
@@ -446,6 +525,8 @@ void slab_free(nns_handle *h) {
     if (S->comm && nccl_api()) nccl_api()->CommDestroy(S->comm);
     cudaFree(S->d_cprime); cudaFree(S->d_p0); cudaFree(S->d_flags);
     for (double *d : S->d_own) cudaFree(d);
+    for (int d = 0; d < 2; ++d) if (S->peer_box[d]) cudaIpcCloseMemHandle(S->peer_box[d]);
+    cudaFree(S->d_box);
     if (S->h_flags) cudaFreeHost(S->h_flags);
     if (S->ev[0]) cudaEventDestroy(S->ev[0]);
     if (S->ev[1]) cudaEventDestroy(S->ev[1]);
@@ -491,6 +572,46 @@ int slab_attach(nns_handle *h, int rank, int nranks, const unsigned char *id128)
     NNS_CUDA(cudaMallocHost(&S->h_flags, sizeof(int) * 64));
     NNS_CUDA(cudaEventCreate(&S->ev[0]));
     NNS_CUDA(cudaEventCreate(&S->ev[1]));
+    return NNS_OK;
+}
+
+// Peer-memory mailboxes: every rank allocates one, exports its 64-byte IPC handle, and maps the mailboxes of the
+// ranks above and below (handles travel through torch.distributed).  With both mapped, the tick loop of the
+// SOR exchanges its rows with NVLink stores + flags (run_sweeps) instead of NCCL launches.
+int slab_ipc_export(nns_handle *h, unsigned char *handle64) {
+    SlabState *S = static_cast<SlabState *>(h->slab);
+    if (!S) { set_error("slab path: call nns_slab_attach first"); return NNS_ERR_INVALID; }
+    if (!S->d_box) {
+        NNS_CUDA(cudaMalloc(&S->d_box, box_bytes(h->g.ny)));
+        NNS_CUDA(cudaMemset(S->d_box, 0, box_bytes(h->g.ny)));
+    }
+    cudaIpcMemHandle_t hd;
+    NNS_CUDA(cudaIpcGetMemHandle(&hd, S->d_box));
+    static_assert(sizeof(hd) == 64, "IPC handle size");
+    memcpy(handle64, &hd, 64);
+    return NNS_OK;
+}
+
+int slab_ipc_connect(nns_handle *h, const unsigned char *above64, const unsigned char *below64) {
+    SlabState *S = static_cast<SlabState *>(h->slab);
+    if (!S || !S->d_box) { set_error("slab path: call nns_slab_ipc_export first"); return NNS_ERR_INVALID; }
+    const unsigned char *hs[2] = {above64, below64};
+    const bool need[2] = {S->rank > 0, S->rank < S->nranks - 1};
+    for (int d = 0; d < 2; ++d) {
+        if (!need[d]) continue;
+        if (!hs[d]) { set_error("slab ipc connect: missing neighbour handle"); return NNS_ERR_INVALID; }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, hs[d], 64);
+        void *ptr = nullptr;
+        NNS_CUDA(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+        S->peer_box[d] = static_cast<unsigned char *>(ptr);
+    }
+    cudaDriverEntryPointQueryResult qr;
+    void *fn = nullptr;
+    NNS_CUDA(cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr));
+    if (!fn || qr != cudaDriverEntryPointSuccess) { set_error("cuStreamWaitValue32 is not available"); return NNS_ERR_UNSUPPORTED; }
+    *reinterpret_cast<void **>(&S->StreamWaitValue32) = fn;
+    S->p2p = true;
     return NNS_OK;
 }
 

@@ -33,7 +33,7 @@ class SlabChorin:
     """chorin_fd (explicit) on this rank's slab of an (nx, ny) grid."""
 
     def __init__(self, nx, ny, *, u_bc, v_bc, p_bc, nit=50, dt=0.001, rho=1, nu=0.1, beta=1.25, rank=None, world=None,
-                 device=None, check_finite=False):
+                 device=None, check_finite=False, p2p=True):
         if not torch.cuda.is_available():
             raise RuntimeError("nns_b200 slabs need a CUDA device (no CPU fallback)")
         import torch.distributed as dist
@@ -54,6 +54,23 @@ class SlabChorin:
             idbuf = np.frombuffer(box[0], dtype=np.uint8).copy()
         with torch.cuda.device(self.device):
             _lib.check(self._L.nns_slab_attach(self.handle.h, rank, world, idbuf.ctypes.data))
+        self.p2p = False
+        if world > 1 and p2p:
+            # peer-memory mailboxes for the per-tick exchange of p (CUDA IPC handles travel through torch.distributed)
+            mine = np.zeros(64, dtype=np.uint8)
+            _lib.check(self._L.nns_slab_ipc_export(self.handle.h, mine.ctypes.data))
+            allh = [None] * world
+            dist.all_gather_object(allh, mine.tobytes())
+            nb = [np.frombuffer(allh[r], dtype=np.uint8).copy() if 0 <= r < world else None for r in (rank - 1, rank + 1)]
+            ptr = lambda a: None if a is None else a.ctypes.data  # noqa: E731
+            with torch.cuda.device(self.device):
+                rc = self._L.nns_slab_ipc_connect(self.handle.h, ptr(nb[0]), ptr(nb[1]))
+            ok = torch.tensor([1 if rc == 0 else 0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # all ranks use the same exchange
+            if int(ok.item()) != 1:
+                raise RuntimeError("CUDA IPC peer mapping failed on some rank (%s); construct SlabChorin(p2p=False) to "
+                                   "use NCCL send/recv in the tick loop" % self._L.nns_last_error().decode())
+            self.p2p = True
         self.row0, self.nrows = partition(nx, world, rank)
         z = lambda: torch.zeros((self.nrows + 2, ny), dtype=torch.float64, device=self.device)  # noqa: E731
         self.u, self.v, self.p, self.u1, self.v1, self._un, self._vn = z(), z(), z(), z(), z(), z(), z()
