@@ -29,9 +29,12 @@ namespace {
 
 constexpr int NT_ST = 128;      // threads of the stencil role (1 warpgroup)
 constexpr int GR = 4;           // rows per ring group (one bulk copy per field, one full/empty mbarrier pair)
-constexpr int NG = 2;           // groups in the ring (double buffer)
+constexpr int NG = 2;           // groups in the ring of the legacy kernel (double buffer)
+constexpr int NGW = 8;          // groups in the ring of the wave kernel (C' lives in Tensor Memory: room for a deep ring)
 constexpr int RING = GR * NG;   // rows per field in the stencil ring
 constexpr int REGS_SOR = 200, REGS_ST = 104;
+constexpr int REGS_SOR_W = 200, REGS_ST_W = 104;     // setmaxnreg only moves registers inside the CTA's launch allocation (384 x 168)
+constexpr int NW_SOR = NT_SOR / 32;
 
 // named barrier ids (0 is __syncthreads)
 enum { BAR_SOR = 1, BAR_ST = 2, BAR_READY = 3, BAR_CONSUMED = 5, BAR_DONE = 7 };   // +0/+1 by member parity
@@ -61,12 +64,28 @@ struct StreamArgs {
     size_t traj_member_stride, traj_off;   // element offsets: member stride, offset of this step
     int32_t *sweeps;         // [count] or null
     unsigned long long *nonfinite;
-    long long *prof;         // optional [gridDim.x][16] phase cycle counters (NNS_STREAM_PROF=1)
+    long long *prof;         // optional [gridDim.x][NPROF] phase cycle counters (NNS_STREAM_PROF=1)
+    // legacy kernel as the re-run pass of the wave kernel: members list[0 .. *list_count) instead of 0 .. count
+    const int *list;
+    const int *list_count;
+    // wave kernel
+    int *redo_list;          // members whose SOR loop stops early (or undecided by the fast test): re-run pass
+    int *redo_count;
+    double *pscr;            // [gridDim.x][2][NX*NY] SOR results before p_bc (L2-resident scratch)
+    int wamin[NW_SOR], wrange[NW_SOR];   // per SOR warp: first block diagonal and spread of its lanes
+    int rmax;                // largest spread
+    long long *trace;        // optional (NNS_WAVE_TRACE=1): clock64 of CTA 0 per SOR warp at sweep start / barrier arrival / release
 };
 
 // phase timers: thread `lead` of a role accumulates clock64() deltas into prof[slot]
+constexpr int NPROF = 32;
+#ifdef NNS_STREAM_PROF_FINE      // timers inside the stencil passes: they cost registers even when switched off at run time
+#define NNS_FINE(...) __VA_ARGS__
+#else
+#define NNS_FINE(...)
+#endif
 #define NNS_PROF_T() (a.prof ? clock64() : 0ll)
-#define NNS_PROF_ADD(slot, t0) do { if (a.prof && lead) a.prof[(size_t)blockIdx.x * 16 + (slot)] += clock64() - (t0); } while (0)
+#define NNS_PROF_ADD(slot, t0) do { if (a.prof && lead) a.prof[(size_t)blockIdx.x * NPROF + (slot)] += clock64() - (t0); } while (0)
 
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -196,7 +215,7 @@ struct Cfg {
 // A row needs the row below it, so a step works on rows [GR*g - 1, GR*g + GR - 1): the east / west
 // operands of the lagging row GR*g - 1 are saved in registers before its group is released.
 // ----------------------------------------------------------------------------------------------
-template <int NY>
+template <int NY, int NG>
 struct Ring {
     double *buf;          // [NG][4][GR][NY]
     uint64_t *full;       // [NG]
@@ -249,8 +268,9 @@ __device__ __forceinline__ void store_cprime(double *img, const short *tidmap, c
 }
 
 // pass 1: predictor of member m -> un, vn (global) and the C' image.
-template <typename C>
-__device__ void stencil_pass1(const StreamArgs &a, Ring<C::NY> &ring, const short *s_ord, int m, int ts, double *img) {
+template <typename C, int NGR>
+__device__ void stencil_pass1(const StreamArgs &a, Ring<C::NY, NGR> &ring, const short *s_ord, const short *s_tid, int m, int mnext, int ts,
+                              double *img) {
 #ifdef NNS_ABL_NOSTENCIL      // timing ablation: the SOR role alone on the SM
     return;
 #endif
@@ -275,15 +295,19 @@ __device__ void stencil_pass1(const StreamArgs &a, Ring<C::NY> &ring, const shor
     const bool jin = j > 0 && j < NY - 1;
     const int bj = jin ? (j - 1) / C::BCc : 0, lj = jin ? (j - 1) - bj * C::BCc : 0;
 
+    NNS_FINE(const bool lead = ts == 0; long long tp0 = NNS_PROF_T(), twait = 0;)
     // pull the next member's pressure towards L2 while we are at it (the SOR role loads it soon)
-    if (m + (int)gridDim.x < a.count) {
-        const char *pp = reinterpret_cast<const char *>(a.p + (size_t)(m + gridDim.x) * N);
+    if (mnext >= 0) {
+        const char *pp = reinterpret_cast<const char *>(a.p + (size_t)mnext * N);
         for (size_t off = (size_t)ts * 128; off < N * sizeof(double); off += (size_t)NT_ST * 128)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + off));
     }
-    if (ts == 0) { ring.template issue<4>(0, src); ring.template issue<4>(1, src); }
-    ring.template prefetch_l2<4>(2, src, ts);
-    ring.template prefetch_l2<4>(3, src, ts);
+    if (ts == 0) {
+#pragma unroll
+        for (int g = 0; g < NGR; ++g) ring.template issue<4>(g, src);
+    }
+    ring.template prefetch_l2<4>(NGR, src, ts);
+    ring.template prefetch_l2<4>(NGR + 1, src, ts);
 
     double uN = 0, uC = 0, uS = 0, vN = 0, vC = 0, vS = 0, aN = 0, aC = 0, aS = 0, bN = 0, bC = 0, bS = 0;
     double uE = 0, uW = 0, vE = 0, vW = 0, aE = 0, aW = 0, bE = 0, bW = 0;   // east / west operands of the current row
@@ -291,6 +315,7 @@ __device__ void stencil_pass1(const StreamArgs &a, Ring<C::NY> &ring, const shor
     int bi = 0, li = -1, tsor = 0;           // block row / row inside the block of the current row, owning SOR thread
 
     // one row: (uC..) is row i, (uS..) row i+1, (uE, uW..) the east / west neighbours of row i
+    // (a branch-free variant -- selects instead of the interior test -- measured slower: 4.79 vs 4.60 ms/step)
     auto do_row = [&](int i) {
         double ru = uC, rv = vC;
         const bool interior = jin && i > 0 && i < NX - 1;
@@ -311,7 +336,7 @@ __device__ void stencil_pass1(const StreamArgs &a, Ring<C::NY> &ring, const shor
         const double rv_w = __shfl_up_sync(0xffffffffu, rv, 1);
         if (i >= 1 && i < NX - 1) {
             if (++li == C::BRc) { li = 0; ++bi; }
-            if (li == 0 && jin) tsor = a.tidmap[bi * C::NBCc + bj];
+            if (li == 0 && jin) tsor = s_tid[bi * C::NBCc + bj];
             if (jin && lane > 0) {
                 const double c = cc * (cu * (ru - ru_prev) + cv * (rv - rv_w));
                 const int q = s_ord[li * C::BCc + lj];
@@ -321,8 +346,11 @@ __device__ void stencil_pass1(const StreamArgs &a, Ring<C::NY> &ring, const shor
         ru_prev = ru;
     };
     const int jw = j > 0 ? j - 1 : j, je = j < NY - 1 ? j + 1 : j;
+    NNS_FINE(NNS_PROF_ADD(16, tp0); tp0 = NNS_PROF_T();)
     for (int g = 0; g < NGROUPS; ++g) {
+        NNS_FINE(const long long tw0 = NNS_PROF_T();)
         ring.wait_full(g);
+        NNS_FINE(if (a.prof) twait += clock64() - tw0;)
 #pragma unroll
         for (int r = -1; r < GR - 1; ++r) {              // rows GR*g - 1 .. GR*g + GR - 2
             const int i = g * GR + r;
@@ -340,23 +368,25 @@ __device__ void stencil_pass1(const StreamArgs &a, Ring<C::NY> &ring, const shor
         uE = ring.row(g, 0, GR - 1)[je]; uW = ring.row(g, 0, GR - 1)[jw]; vE = ring.row(g, 1, GR - 1)[je]; vW = ring.row(g, 1, GR - 1)[jw];
         aE = ring.row(g, 2, GR - 1)[je]; aW = ring.row(g, 2, GR - 1)[jw]; bE = ring.row(g, 3, GR - 1)[je]; bW = ring.row(g, 3, GR - 1)[jw];
         ring.release(g);
-        if (g + 2 < NGROUPS) {
-            if (ts == 0) ring.template issue<4>(g + 2, src);
-            if (g + 4 < NGROUPS) ring.template prefetch_l2<4>(g + 4, src, ts);
+        if (g + NGR < NGROUPS) {
+            if (ts == 0) ring.template issue<4>(g + NGR, src);
+            if (g + NGR + 2 < NGROUPS) ring.template prefetch_l2<4>(g + NGR + 2, src, ts);
         }
     }
     uN = uC; vN = vC; uC = uS; vC = vS;                    // last row (an edge: copied)
     do_row(NX - 1);
     ring.g0 += NGROUPS;
+    NNS_FINE(NNS_PROF_ADD(18, tp0); if (a.prof && lead) a.prof[(size_t)blockIdx.x * NPROF + 17] += twait; tp0 = NNS_PROF_T();)
     __threadfence_block();
     named_sync(BAR_ST, NT_ST);
     st_apply_bc_global(un, NX, NY, a.ubc, bcval, dx, dy, ts);
     st_apply_bc_global(vn, NX, NY, a.vbc, bcval, dx, dy, ts);
+    NNS_FINE(NNS_PROF_ADD(19, tp0); tp0 = NNS_PROF_T();)
     // patch C' where an operand is a boundary line (row 1, column 1) or belongs to another warp's lane 31
     auto patch = [&](int i, int jj) {
         const size_t gq = (size_t)i * NY + jj;
         const double c = cc * (cu * (un[gq] - un[gq - NY]) + cv * (vn[gq] - vn[gq - 1]));
-        store_cprime<C>(img, a.tidmap, s_ord, i, jj, c);
+        store_cprime<C>(img, s_tid, s_ord, i, jj, c);
     };
     if (jin) patch(1, j);
     for (int i = 2 + ts; i < NX - 1; i += NT_ST) {
@@ -366,19 +396,34 @@ __device__ void stencil_pass1(const StreamArgs &a, Ring<C::NY> &ring, const shor
             if (32 * w < NY - 1) patch(i, 32 * w);
     }
     __threadfence();                      // the image is pulled through L2 (cp.async.cg) by the SOR role
+    NNS_FINE(NNS_PROF_ADD(20, tp0);)
 }
 
 // pass 2: p_bc, projection and trajectory snapshot of member m.
-template <typename C>
-__device__ void stencil_pass2(const StreamArgs &a, Ring<C::NY> &ring, int m, int ts) {
+// psrc: where the SOR role left its result -- the member's own p (legacy kernel: in place) or the CTA's scratch
+// image (wave kernel: the edges are copied in from p first, and every row of the final p is written back here,
+// coalesced, so that the member's p stays untouched until its sweep count is known).
+template <typename C, int NGR, bool SCR>
+__device__ void stencil_pass2(const StreamArgs &a, Ring<C::NY, NGR> &ring, int m, int ts, double *pscr = nullptr) {
 #ifdef NNS_ABL_NOSTENCIL
     return;
 #endif
     constexpr int NX = C::NX, NY = C::NY, NGROUPS = NX / GR;
     const size_t N = (size_t)NX * NY;
-    double *pg = a.p + m * N, *un = a.un + m * N, *vn = a.vn + m * N;
+    double *pout = a.p + m * N, *un = a.un + m * N, *vn = a.vn + m * N;
+    double *pg = SCR ? pscr : pout;
+    NNS_FINE(const bool lead = ts == 0; long long tp0 = NNS_PROF_T(), twait = 0;)
     const double *bcval = a.bcval ? a.bcval + (size_t)m * a.n_bcs : nullptr;
     const double dt = a.g.dt, dx = a.g.dx, dy = a.g.dy;
+    if (SCR) {
+        static_assert(NX == NT_ST && NY == NT_ST, "edge copy maps one thread to one edge cell per side");
+        pg[ts] = pout[ts];
+        pg[(size_t)(NX - 1) * NY + ts] = pout[(size_t)(NX - 1) * NY + ts];
+        pg[(size_t)ts * NY] = pout[(size_t)ts * NY];
+        pg[(size_t)ts * NY + NY - 1] = pout[(size_t)ts * NY + NY - 1];
+        __threadfence_block();
+        named_sync(BAR_ST, NT_ST);
+    }
     st_apply_bc_global(pg, NX, NY, a.pbc, bcval, dx, dy, ts);
     __threadfence();                      // generic-proxy writes of p / un / vn (this CTA) before the bulk reads
     named_sync(BAR_ST, NT_ST);
@@ -390,8 +435,8 @@ __device__ void stencil_pass2(const StreamArgs &a, Ring<C::NY> &ring, int m, int
     const size_t toff = (size_t)m * a.traj_member_stride + a.traj_off;
     if (ts == 0) {
         fence_proxy_async();
-        ring.template issue<3>(0, src);
-        ring.template issue<3>(1, src);
+#pragma unroll
+        for (int g = 0; g < NGR; ++g) ring.template issue<3>(g, src);
     }
     double pN = 0, pC = 0, pS = 0, pE = 0, pW = 0, ruC = 0, rvC = 0, ruS = 0, rvS = 0;
     unsigned long long bad = 0;
@@ -404,11 +449,15 @@ __device__ void stencil_pass2(const StreamArgs &a, Ring<C::NY> &ring, int m, int
             un[q] = ru;
             vn[q] = rv;
         }
+        if (SCR) pout[q] = pC;
         if (a.traj_u) { a.traj_u[toff + q] = ru; a.traj_v[toff + q] = rv; a.traj_p[toff + q] = pC; }
         if (a.flags & NNS_FLAG_CHECK_FINITE) bad += !(isfinite(ru) && isfinite(rv) && isfinite(pC));
     };
+    NNS_FINE(NNS_PROF_ADD(21, tp0); tp0 = NNS_PROF_T();)
     for (int g = 0; g < NGROUPS; ++g) {
+        NNS_FINE(const long long tw0 = NNS_PROF_T();)
         ring.wait_full(g);
+        NNS_FINE(if (a.prof) twait += clock64() - tw0;)
 #pragma unroll
         for (int r = -1; r < GR - 1; ++r) {
             const int i = g * GR + r;
@@ -419,11 +468,12 @@ __device__ void stencil_pass2(const StreamArgs &a, Ring<C::NY> &ring, int m, int
         }
         pE = ring.row(g, 0, GR - 1)[je]; pW = ring.row(g, 0, GR - 1)[jw];
         ring.release(g);
-        if (ts == 0 && g + 2 < NGROUPS) ring.template issue<3>(g + 2, src);
+        if (ts == 0 && g + NGR < NGROUPS) ring.template issue<3>(g + NGR, src);
     }
     pN = pC; pC = pS; ruC = ruS; rvC = rvS;
     do_row(NX - 1);
     ring.g0 += NGROUPS;
+    NNS_FINE(NNS_PROF_ADD(23, tp0); if (a.prof && lead) a.prof[(size_t)blockIdx.x * NPROF + 22] += twait;)
     if ((a.flags & NNS_FLAG_CHECK_FINITE) && bad) atomicAdd(a.nonfinite, bad);
 }
 
@@ -434,7 +484,8 @@ struct CfgX : Cfg<BR, BC, NBR, NBC> {
     static constexpr int RSc = (BR + 1) / 2;       // rows of the top sub-block
 };
 
-template <typename C>
+// LIST: the members are list[0 .. *list_count) (re-run pass of the wave kernel) instead of 0 .. count
+template <typename C, bool LIST>
 __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const StreamArgs a) {
     constexpr int BR = C::BRc, BC = C::BCc, RS = C::RSc, NX = C::NX, NY = C::NY, NCH = C::NCH;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -449,7 +500,9 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
 
     const int tid = threadIdx.x;
     const size_t N = (size_t)NX * NY;
-    const int nmine = a.count > (int)blockIdx.x ? (a.count - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int total = LIST ? *a.list_count : a.count;
+    const int nmine = total > (int)blockIdx.x ? (total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    auto member = [&](int k) { const int idx = (int)blockIdx.x + k * (int)gridDim.x; return LIST ? a.list[idx] : idx; };
     double *img = a.cimg + (size_t)blockIdx.x * 2 * NCH * NT_SOR;
 
     if (tid == 0) {
@@ -465,20 +518,20 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
         // =============================== stencil role ===========================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_ST));
         const int ts = tid - NT_SOR;
-        Ring<NY> ring{ringbuf, s_full, s_empty, 0u};
+        Ring<NY, NG> ring{ringbuf, s_full, s_empty, 0u};
         const bool lead = ts == 0;
         long long t0 = NNS_PROF_T();
-        stencil_pass1<C>(a, ring, s_ord, blockIdx.x, ts, img);
+        stencil_pass1<C, NG>(a, ring, s_ord, a.tidmap, member(0), nmine > 1 ? member(1) : -1, ts, img);
         NNS_PROF_ADD(8, t0);
         named_arrive(BAR_READY + 0, NT_SOR + NT_ST);
         for (int k = 0; k < nmine; ++k) {
-            const int m = blockIdx.x + k * gridDim.x;
+            const int m = member(k);
             if (k + 1 < nmine) {
                 t0 = NNS_PROF_T();
                 named_sync(BAR_CONSUMED + (k & 1), NT_SOR + NT_ST);       // the SOR role has pulled image k
                 NNS_PROF_ADD(9, t0);
                 t0 = NNS_PROF_T();
-                stencil_pass1<C>(a, ring, s_ord, m + gridDim.x, ts, img);
+                stencil_pass1<C, NG>(a, ring, s_ord, a.tidmap, member(k + 1), k + 2 < nmine ? member(k + 2) : -1, ts, img);
                 NNS_PROF_ADD(8, t0);
                 named_arrive(BAR_READY + ((k + 1) & 1), NT_SOR + NT_ST);
             }
@@ -486,7 +539,7 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
             named_sync(BAR_DONE + (k & 1), NT_SOR + NT_ST);               // SOR of member k finished, p written
             NNS_PROF_ADD(10, t0);
             t0 = NNS_PROF_T();
-            stencil_pass2<C>(a, ring, m, ts);
+            stencil_pass2<C, NG, false>(a, ring, m, ts);
             NNS_PROF_ADD(11, t0);
         }
     } else {
@@ -514,7 +567,7 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
         const int tmax = 2 * C::NBRc + C::NBCc - 2 + 2 * (cap - 1);      // last sub-block diagonal + 2 (cap - 1)
 
         for (int kk = 0; kk < nmine; ++kk) {
-            const int m = blockIdx.x + kk * gridDim.x;
+            const int m = member(kk);
             double *pg = a.p + (size_t)m * N;
             double P[BR][BC];
             auto load_block = [&]() {
@@ -583,7 +636,7 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
                 };
                 unsigned long long mask = 0ull, amb = 0ull;
                 wavefront<BR, BC, RS, 1>(P, Cme, h, owner, ds.bd, tmax, cap, k, tolbits, mask, amb,
-                                     a.prof && (tid == 0 || tid == 128) ? a.prof + (size_t)blockIdx.x * 16 + 12 + (tid >> 6) : nullptr);
+                                     a.prof && (tid == 0 || tid == 128) ? a.prof + (size_t)blockIdx.x * NPROF + 12 + (tid >> 6) : nullptr);
                 NNS_PROF_ADD(3, t0);
                 t0 = NNS_PROF_T();
                 need = sweeps_needed(mask, amb);
@@ -622,6 +675,318 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
     }
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// Wave kernel: the same two roles, but the SOR wavefront runs CONTINUOUSLY across the members of a CTA.
+//
+//  * Sub-block (sbi, bj) performs sweep s of the CTA's k-th member at super-stage sbi + bj + 2s + PER*k with
+//    PER = 2*(nit-1) + R + 1 (R = largest spread of block diagonals inside one warp): while the blocks at the
+//    bottom right finish member k, the blocks at the top left already sweep member k+1.  Members change per
+//    WARP (all lanes of a warp work on the same member, lanes outside the band are predicated off), so every
+//    branch and every Tensor Memory access is warp-uniform.  113 super-stages per member instead of 141, and
+//    no serial load / pull / reduce / store phases.
+//  * The right-hand side C' lives in TENSOR MEMORY (256 KB per SM, otherwise idle in this kernel): 128 columns
+//    per thread and member, double-buffered; tcgen05.ld in the sweeps (block_sweep_tm), tcgen05.st by the
+//    stencil warp of the same SM sub-partition (lane quarter), which forwards the C' image of the next member.
+//    The SOR role never touches C' traffic, and the single shared-memory pipe only carries the block halos.
+//  * Shared memory: halo slots (64 KiB) + an 8-deep TMA row ring (128 KiB) for the stencil role.
+//  * A warp that has finished its member stores its p blocks to an L2-resident scratch image, starts the loads
+//    of the next member's blocks and start halos (cp.async straight into the neighbours' slots, which nobody
+//    reads any more), and one idle super-stage later publishes its exit-test flags.  The stencil role turns
+//    the scratch image into the final p (p_bc, projection) once all eight warps have reported; if the flags say
+//    that the reference loop would have stopped early (or the fast test is undecided), the member's p is still
+//    untouched and the member is queued for the legacy kernel, which re-runs it with the exact sweep count.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void spin_until_ge(const volatile int *p, int v) {
+    while (*p < v) __nanosleep(32);
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void tm_st16(uint32_t taddr, const double2 (&v)[4]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(__double2loint(v[0].x)), "r"(__double2hiint(v[0].x)), "r"(__double2loint(v[0].y)), "r"(__double2hiint(v[0].y)),
+        "r"(__double2loint(v[1].x)), "r"(__double2hiint(v[1].x)), "r"(__double2loint(v[1].y)), "r"(__double2hiint(v[1].y)),
+        "r"(__double2loint(v[2].x)), "r"(__double2hiint(v[2].x)), "r"(__double2loint(v[2].y)), "r"(__double2hiint(v[2].y)),
+        "r"(__double2loint(v[3].x)), "r"(__double2hiint(v[3].x)), "r"(__double2loint(v[3].y)), "r"(__double2hiint(v[3].y))
+        : "memory");
+}
+__device__ __forceinline__ double2 ld_cg_f64x2(const double2 *p) {
+    double2 v;
+    asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+template <typename C>
+struct WaveSmem {
+    static constexpr size_t H_BYTES = C::H_BYTES;
+    static constexpr size_t RING_BYTES = sizeof(double) * GR * NGW * 4 * C::NY;
+    static constexpr size_t SMEM_BYTES = H_BYTES + RING_BYTES;
+};
+
+template <typename C>
+__global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_wave_kernel(const StreamArgs a) {
+    constexpr int BR = C::BRc, BC = C::BCc, RS = C::RSc, NX = C::NX, NY = C::NY, NCH = C::NCH;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned long long s_mask[2][2];       // [member parity][violated, undecided] sweep bit sets
+    __shared__ volatile int s_cready[NW_SOR];          // members whose C' has been delivered to the warp's Tensor Memory
+    __shared__ volatile int s_wdone[NW_SOR];           // members the warp has finished sweeping (its C' buffer is free)
+    __shared__ volatile int s_wstored[NW_SOR];         // members whose p blocks and exit flags of the warp are visible
+    __shared__ int s_need;
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_full[NGW], s_empty[NGW];
+    __shared__ short s_ord[128];
+    __shared__ short s_tid[C::NB];
+
+    double *H = reinterpret_cast<double *>(smem_raw);
+    double *ringbuf = reinterpret_cast<double *>(smem_raw + WaveSmem<C>::H_BYTES);
+
+    const int tid = threadIdx.x;
+    const size_t N = (size_t)NX * NY;
+    const int nmine = a.count > (int)blockIdx.x ? (a.count - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    double *img = a.cimg + (size_t)blockIdx.x * 2 * NCH * NT_SOR;
+    double *pscr = a.pscr + (size_t)blockIdx.x * 2 * N;
+    if (nmine == 0) return;
+
+    if (tid == 0) {
+        for (int r = 0; r < NGW; ++r) { mbar_init(&s_full[r], 1); mbar_init(&s_empty[r], NT_ST / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_mask[0][0] = s_mask[0][1] = s_mask[1][0] = s_mask[1][1] = 0ull;
+    }
+    if (tid < NW_SOR) { s_cready[tid] = 0; s_wdone[tid] = 0; s_wstored[tid] = 0; }
+    if (tid < 128) s_ord[tid] = c_ord[tid];
+    if (tid < C::NB) s_tid[tid] = a.tidmap[tid];
+    if (tid < 32) {         // the whole Tensor Memory of the SM (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = s_tmem;
+    const int cap = a.g.nit - 1;
+
+    if (tid >= NT_SOR) {
+        // =============================== stencil role ===========================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_ST_W));
+        const int ts = tid - NT_SOR, sw = ts >> 5, lane = ts & 31;
+        Ring<NY, NGW> ring{ringbuf, s_full, s_empty, 0u};
+        const bool lead = ts == 0;
+        // forward the C' image of the CTA's k-th member into the Tensor Memory of the two SOR warps that share
+        // this warp's lane quarter (SOR warps sw and sw + 4)
+        auto fill = [&](int k) {
+            named_sync(BAR_ST, NT_ST);          // the image is complete (global writes of all stencil threads)
+#pragma unroll 1
+            for (int hh = 0; hh < 2; ++hh) {
+                const int hw = sw + 4 * hh;
+                spin_until_ge(&s_wdone[hw], k - 1);         // buffer k & 1 was last read for member k - 2
+                const uint32_t taddr = tmem + ((uint32_t)(32 * sw) << 16) + (uint32_t)(256 * hh + 128 * (k & 1));
+                const double2 *gi = reinterpret_cast<const double2 *>(img) + hw * 32 + lane;
+#pragma unroll 2
+                for (int c = 0; c < NCH; c += 4) {
+                    double2 v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[e] = ld_cg_f64x2(gi + (size_t)(c + e) * NT_SOR);
+                    tm_st16(taddr + 4 * c, v);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) s_cready[hw] = k + 1;
+            }
+            named_sync(BAR_ST, NT_ST);          // the image may be overwritten by the next pass 1
+        };
+        long long t0 = NNS_PROF_T();
+        stencil_pass1<C, NGW>(a, ring, s_ord, s_tid, blockIdx.x, nmine > 1 ? (int)(blockIdx.x + gridDim.x) : -1, ts, img);
+        NNS_PROF_ADD(8, t0);
+        fill(0);
+        for (int k = 0; k < nmine; ++k) {
+            const int m = blockIdx.x + k * gridDim.x;
+            if (k + 1 < nmine) {
+                t0 = NNS_PROF_T();
+                stencil_pass1<C, NGW>(a, ring, s_ord, s_tid, m + gridDim.x, k + 2 < nmine ? (int)(m + 2 * gridDim.x) : -1, ts, img);
+                NNS_PROF_ADD(8, t0);
+                t0 = NNS_PROF_T();
+                fill(k + 1);
+                NNS_PROF_ADD(9, t0);
+            }
+            t0 = NNS_PROF_T();
+            if (ts < NW_SOR) spin_until_ge(&s_wstored[ts], k + 1);       // all eight warps have reported member k
+            __threadfence();
+            named_sync(BAR_ST, NT_ST);
+            if (ts == 0) {
+                // number of sweeps the reference loop runs (chorin_fd:183-199): the first sweep without a certain
+                // violation decides; if it is merely undecided by the fast test the re-run pass decides exactly
+                const unsigned long long full = cap >= 64 ? ~0ull : ((1ull << cap) - 1ull);
+                const unsigned long long viol = s_mask[k & 1][0], und = s_mask[k & 1][1] & ~viol & full;
+                const unsigned long long clr = ~viol & full;
+                int nd = clr ? __ffsll((long long)clr) : cap;
+                if (clr && ((und >> (nd - 1)) & 1ull)) nd = -1;
+                s_need = nd;
+                s_mask[k & 1][0] = 0ull; s_mask[k & 1][1] = 0ull;
+            }
+            named_sync(BAR_ST, NT_ST);
+            const int need = s_need;
+            NNS_PROF_ADD(10, t0);
+            t0 = NNS_PROF_T();
+#if defined(NNS_ABL_NOSWEEP) || defined(NNS_ABL_NOSTENCIL)
+            if (true) {
+#else
+            if (need == cap) {
+#endif
+                stencil_pass2<C, NGW, true>(a, ring, m, ts, pscr + (size_t)(k & 1) * N);
+                if (a.sweeps && ts == 0) a.sweeps[m] = need;
+            } else if (ts == 0) {
+                a.redo_list[atomicAdd(a.redo_count, 1)] = m;
+            }
+            NNS_PROF_ADD(11, t0);
+        }
+    } else {
+        // ================================= SOR role =============================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_SOR_W));
+        SBlock ds = a.desc[tid];
+        const bool owner = ds.r0 > 0;
+        const int w = tid >> 5, lane = tid & 31;
+        if (!owner) { ds.r0 = 1; ds.c0 = 1; }
+        const int r0 = ds.r0, c0 = ds.c0;
+        SHalo<BR, BC> h;
+        h.Hme = H + tid;
+        h.pubT = ds.nN >= 0; h.pubB = ds.nS >= 0; h.pubL = ds.nW >= 0; h.pubR = ds.nE >= 0;
+        h.hN = h.pubT ? H + BC * NT_SOR + ds.nN : H + tid;
+        h.hS = h.pubB ? H + ds.nS : H + BC * NT_SOR + tid;
+        h.hW = h.pubL ? H + (2 * BC + BR) * NT_SOR + ds.nW : H + 2 * BC * NT_SOR + tid;
+        h.hE = h.pubR ? H + 2 * BC * NT_SOR + ds.nE : H + (2 * BC + BR) * NT_SOR + tid;
+        if (!owner) { h.pubT = h.pubB = h.pubL = h.pubR = false; }
+
+        const double dx = a.g.dx, dy = a.g.dy, beta = a.g.beta;
+        const double dx2 = dx * dx, dy2 = dy * dy, den = 2.0 * dx2 + 2.0 * dy2;
+        Coef k;
+        k.ca = beta * dy2 / den; k.cb = beta * dx2 / den; k.cc = -beta; k.cu = 0; k.cv = 0; k.beta = beta; k.tol = a.g.tol;
+        const unsigned tolhi = (unsigned)((unsigned long long)__double_as_longlong(a.g.tol) >> 32);
+        const int amin = a.wamin[w], last = 2 * cap - 1 + a.wrange[w];      // last local stage with an active lane
+        const int per = 2 * cap + a.rmax + 1;
+        const int delta = owner ? ds.bd - amin : (1 << 20);                 // the lane's band starts delta stages later
+        int tend = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < NW_SOR; ++w2) tend = max(tend, a.wamin[w2] + 2 * cap + a.wrange[w2]);   // last report stage of a member
+        tend += per * (nmine - 1);
+        const uint32_t tm_mine = tmem + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(256 * (w >> 2));
+        const bool lead = tid == 0;
+
+        double P[BR][BC];
+        // loads of a member's blocks and of the start values on the far side of the block's south and east edges
+        // (and of the frozen boundary values for blocks at the wall): registers / cp.async into the halo slots
+        auto fetch = [&](int m) {
+            const double *pg = a.p + (size_t)m * N;
+#pragma unroll
+            for (int li = 0; li < BR; ++li)
+#pragma unroll
+                for (int lj = 0; lj < BC; ++lj) P[li][lj] = pg[(size_t)(r0 + li) * NY + c0 + lj];     // (16-byte accesses cost more in register moves than they save)
+            if (owner) {
+#pragma unroll
+                for (int lj = 0; lj < BC; ++lj) {
+                    cp_async8(const_cast<double *>(h.hS) + lj * NT_SOR, pg + (size_t)(r0 + BR) * NY + c0 + lj);
+                    if (!h.pubT) cp_async8(const_cast<double *>(h.hN) + lj * NT_SOR, pg + (size_t)(r0 - 1) * NY + c0 + lj);
+                }
+#pragma unroll
+                for (int li = 0; li < BR; ++li) {
+                    cp_async8(const_cast<double *>(h.hE) + li * NT_SOR, pg + (size_t)(r0 + li) * NY + c0 + BC);
+                    if (!h.pubL) cp_async8(const_cast<double *>(h.hW) + li * NT_SOR, pg + (size_t)(r0 + li) * NY + c0 - 1);
+                }
+            }
+        };
+        unsigned long long mask = 0ull, amb = 0ull;
+        int kw = 0, tl = -amin;
+        long long tsw = 0;
+        const long long tk0 = NNS_PROF_T();
+        for (int T = 0; T <= tend; ++T, ++tl) {
+            if (tl == per) { tl = 0; ++kw; }
+            if (tl >= 0 && kw < nmine) {
+                const int m = blockIdx.x + kw * gridDim.x;
+                if (tl == 0) {
+                    if (kw == 0) fetch(m);
+                    cp_async_wait_all();
+                    const long long t0 = NNS_PROF_T();
+                    spin_until_ge(&s_cready[w], kw + 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    NNS_PROF_ADD(1, t0);
+                    __syncwarp();
+                }
+#ifndef NNS_ABL_NOSWEEP      // timing ablation: the stencil role alone on the SM
+                const bool tracing = a.trace && blockIdx.x == 0 && lane == 0 && kw == 1 && T - per >= 40 && T - per < 56;
+                if (tracing) a.trace[((size_t)w * 16 + (T - per - 40)) * 4 + 0] = clock64();
+                if (tl <= last) {
+                    const long long t0 = NNS_PROF_T();
+                    const int q = tl - delta;
+                    const bool act = q >= 0 && q <= 2 * cap - 1;
+                    const int sidx = q >> 1;
+                    const uint32_t tmc = tm_mine + (uint32_t)(128 * (kw & 1));
+                    unsigned mhi = 0u;
+                    if (!(tl & 1)) block_sweep_tm<BR, BC, RS, 0, RS>(P, tmc, h, k, act, sidx != cap - 1, mhi);
+                    else block_sweep_tm<BR, BC, RS, RS, BR>(P, tmc, h, k, act, sidx != cap - 1, mhi);
+                    if (act) {
+                        mask |= (unsigned long long)(mhi > tolhi) << sidx;
+                        amb |= (unsigned long long)(mhi == tolhi) << sidx;
+                    }
+                    if (a.prof && lane == 0) tsw += clock64() - t0;
+                }
+#endif
+                if (tl == last) {
+                    // the warp has finished member kw: results to the scratch image, next member's loads in flight
+                    double *ps = pscr + (size_t)(kw & 1) * N;
+#ifdef NNS_ABL_NOTRANS       // timing ablation: no block stores / loads at the member changes
+                    if (false) {
+#else
+                    if (owner) {
+#endif
+#pragma unroll
+                        for (int li = 0; li < BR; ++li)
+#pragma unroll
+                            for (int lj = 0; lj < BC; ++lj) ps[(size_t)(r0 + li) * NY + c0 + lj] = P[li][lj];
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) s_wdone[w] = kw + 1;
+#ifndef NNS_ABL_NOTRANS
+                    if (kw + 1 < nmine) fetch(m + gridDim.x);
+#endif
+                }
+                if (tl == last + 1) {
+                    const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)mask), hi = __reduce_or_sync(0xffffffffu, (unsigned)(mask >> 32));
+                    const unsigned alo = __reduce_or_sync(0xffffffffu, (unsigned)amb), ahi = __reduce_or_sync(0xffffffffu, (unsigned)(amb >> 32));
+                    mask = 0ull; amb = 0ull;
+                    // the p blocks of every lane before the warp reports: the readers are threads of this CTA (generic
+                    // proxy) and bulk copies issued by them (async proxy)
+                    __threadfence_block();
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        atomicOr(&s_mask[kw & 1][0], ((unsigned long long)hi << 32) | lo);
+                        atomicOr(&s_mask[kw & 1][1], ((unsigned long long)ahi << 32) | alo);
+                        __threadfence_block();
+                        s_wstored[w] = kw + 1;
+                    }
+                }
+            }
+            const bool tracing2 = a.trace && blockIdx.x == 0 && lane == 0 && kw == 1 && T - per >= 40 && T - per < 56;
+            if (tracing2) a.trace[((size_t)w * 16 + (T - per - 40)) * 4 + 1] = clock64();
+            named_sync(BAR_SOR, NT_SOR);
+            if (tracing2) a.trace[((size_t)w * 16 + (T - per - 40)) * 4 + 2] = clock64();
+        }
+        if (a.prof && lead) {
+            a.prof[(size_t)blockIdx.x * NPROF + 3] += clock64() - tk0;
+            a.prof[(size_t)blockIdx.x * NPROF + 12] += tsw;
+        }
+        if (a.prof && lane == 0) a.prof[(size_t)blockIdx.x * NPROF + 24 + w] += tsw;
+    }
+    // every Tensor Memory access of the CTA is complete
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
 using Cfg128 = CfgX<9, 7, 14, 18>;      // 128 x 128: 126 = 14*9 = 18*7, 252 blocks of 63 cells
 
 struct StreamPlan {
@@ -630,8 +995,13 @@ struct StreamPlan {
     void *d_tab = nullptr;      // desc then tidmap
     double *d_img = nullptr;
     long long *d_prof = nullptr;
+    long long *d_trace = nullptr;
+    double *d_pscr = nullptr;   // wave kernel: [grid][2][NX*NY] SOR results
+    int *d_redo = nullptr;      // wave kernel: [1 + batch] counter, member list of the re-run pass
+    int wamin[NW_SOR] = {0}, wrange[NW_SOR] = {0}, rmax = 0;
     int grid = 0;
     bool ok = false;
+    bool wave = false;
 };
 
 template <typename C>
@@ -675,6 +1045,18 @@ static void build_tables(StreamPlan &pl) {
         d.pad = 0;
         pl.desc[t] = d;
     }
+    // wave kernel: first block diagonal and spread of every SOR warp (members change per warp)
+    pl.rmax = 0;
+    for (int w = 0; w < NW_SOR; ++w) {
+        int lo = 1 << 20, hi = -1;
+        for (int l = 0; l < 32; ++l) {
+            const SBlock &d = pl.desc[(size_t)w * 32 + l];
+            if (d.r0 > 0) { lo = std::min(lo, (int)d.bd); hi = std::max(hi, (int)d.bd); }
+        }
+        pl.wamin[w] = hi < 0 ? 0 : lo;
+        pl.wrange[w] = hi < 0 ? 0 : hi - lo;
+        pl.rmax = std::max(pl.rmax, pl.wrange[w]);
+    }
 }
 
 }  // namespace
@@ -682,19 +1064,36 @@ static void build_tables(StreamPlan &pl) {
 // Debug aid: print and reset the phase counters (NNS_STREAM_PROF=1), averaged over CTAs.
 void chorin_stream_prof_dump(nns_handle *h) {
     StreamPlan *pl = static_cast<StreamPlan *>(h->stream_plan);
+    if (pl && pl->d_trace) {
+        std::vector<long long> t((size_t)NW_SOR * 16 * 4);
+        cudaDeviceSynchronize();
+        cudaMemcpy(t.data(), pl->d_trace, sizeof(long long) * t.size(), cudaMemcpyDeviceToHost);
+        const long long base = t[0];
+        for (int st = 0; st < 16; ++st) {
+            fprintf(stderr, "[nns wave trace] stage %2d:", st);
+            for (int w = 0; w < NW_SOR; ++w) {
+                const long long *e = &t[((size_t)w * 16 + st) * 4];
+                fprintf(stderr, " w%d %lld/%lld/%lld", w, e[0] - base, e[1] - base, e[2] - base);
+            }
+            fprintf(stderr, "\n");
+        }
+    }
     if (!pl || !pl->d_prof) return;
-    std::vector<long long> v((size_t)16 * pl->grid);
+    std::vector<long long> v((size_t)NPROF * pl->grid);
     cudaDeviceSynchronize();
     cudaMemcpy(v.data(), pl->d_prof, sizeof(long long) * v.size(), cudaMemcpyDeviceToHost);
     cudaMemset(pl->d_prof, 0, sizeof(long long) * v.size());
-    static const char *nm[16] = {"sor.load_p", "sor.wait_ready", "sor.pull_cimg", "sor.wavefront", "sor.reduce_redo",
-                                 "sor.store_p", "", "", "st.pass1", "st.wait_consumed", "st.wait_done", "st.pass2",
-                                 "sor.sweep_cyc(t0)", "sor.sweeps(t0)", "sor.sweep_cyc(t128)", "sor.sweeps(t128)"};
-    for (int k = 0; k < 16; ++k) {
+    static const char *nm[NPROF] = {"sor.load_p", "sor.wait_ready", "sor.pull_cimg", "sor.wavefront", "sor.reduce_redo",
+                                    "sor.store_p", "", "", "st.pass1", "st.wait_consumed/fill", "st.wait_done", "st.pass2",
+                                    "sor.sweep_cyc(t0)", "sor.sweeps(t0)", "sor.sweep_cyc(t128)", "sor.sweeps(t128)",
+                                    "p1.prologue", "p1.wait_full", "p1.row_loop", "p1.bcs", "p1.patch", "p2.edges_bcs",
+                                    "p2.wait_full", "p2.row_loop", "sor.sweep_cyc(w0)", "sor.sweep_cyc(w1)", "sor.sweep_cyc(w2)",
+                                    "sor.sweep_cyc(w3)", "sor.sweep_cyc(w4)", "sor.sweep_cyc(w5)", "sor.sweep_cyc(w6)", "sor.sweep_cyc(w7)"};
+    for (int k = 0; k < NPROF; ++k) {
         if (!nm[k][0]) continue;
         double s = 0;
-        for (int b = 0; b < pl->grid; ++b) s += (double)v[(size_t)b * 16 + k];
-        fprintf(stderr, "[nns stream prof] %-18s %12.0f cycles/CTA\n", nm[k], s / pl->grid);
+        for (int b = 0; b < pl->grid; ++b) s += (double)v[(size_t)b * NPROF + k];
+        fprintf(stderr, "[nns stream prof] %-22s %12.0f cycles/CTA\n", nm[k], s / pl->grid);
     }
 }
 
@@ -712,6 +1111,8 @@ void chorin_stream_free(nns_handle *h) {
     cudaFree(pl->d_tab);
     cudaFree(pl->d_img);
     cudaFree(pl->d_prof);
+    cudaFree(pl->d_pscr);
+    cudaFree(pl->d_redo);
     delete pl;
     h->stream_plan = nullptr;
 }
@@ -737,14 +1138,31 @@ int chorin_stream_step(nns_handle *h, const double *uc, const double *vc, const 
             for (int lj = 0; lj < C::BCc; ++lj) ord[li * C::BCc + lj] = (short)split_ord<C::BRc, C::BCc, C::RSc>(li, lj);
         NNS_CUDA(cudaMemcpyToSymbol(c_ord, ord, sizeof(ord)));
         if (getenv("NNS_STREAM_PROF")) {
-            NNS_CUDA(cudaMalloc(&pl->d_prof, sizeof(long long) * 16 * h->sm_count));
-            NNS_CUDA(cudaMemset(pl->d_prof, 0, sizeof(long long) * 16 * h->sm_count));
+            NNS_CUDA(cudaMalloc(&pl->d_prof, sizeof(long long) * NPROF * h->sm_count));
+            NNS_CUDA(cudaMemset(pl->d_prof, 0, sizeof(long long) * NPROF * h->sm_count));
         }
         pl->grid = h->sm_count;
         NNS_CUDA(cudaMalloc(&pl->d_img, sizeof(double2) * C::NCH * NT_SOR * (size_t)pl->grid));
         NNS_CUDA(cudaMemset(pl->d_img, 0, sizeof(double2) * C::NCH * NT_SOR * (size_t)pl->grid));
-        NNS_CUDA(cudaFuncSetAttribute(chorin_stream_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        NNS_CUDA(cudaFuncSetAttribute(chorin_stream_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)C::SMEM_BYTES));
+        // wave kernel (continuous wavefront, C' in Tensor Memory): opt-in with NNS_STREAM_MODE=wave while it is not faster
+        // than the member-at-a-time kernel (4.87 vs 4.60 ms/step on the 4096-member ensemble)
+        const char *mode = getenv("NNS_STREAM_MODE");
+        pl->wave = mode && strcmp(mode, "wave") == 0 && h->g.nit - 1 <= 64;
+        if (pl->wave && getenv("NNS_WAVE_TRACE")) {
+            NNS_CUDA(cudaMalloc(&pl->d_trace, sizeof(long long) * NW_SOR * 16 * 4));
+            NNS_CUDA(cudaMemset(pl->d_trace, 0, sizeof(long long) * NW_SOR * 16 * 4));
+        }
+        if (pl->wave) {
+            NNS_CUDA(cudaFuncSetAttribute(chorin_stream_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)C::SMEM_BYTES));
+            NNS_CUDA(cudaMalloc(&pl->d_pscr, sizeof(double) * 2 * C::NX * C::NY * (size_t)pl->grid));
+            NNS_CUDA(cudaMemset(pl->d_pscr, 0, sizeof(double) * 2 * C::NX * C::NY * (size_t)pl->grid));
+            NNS_CUDA(cudaMalloc(&pl->d_redo, sizeof(int) * (1 + (size_t)h->g.batch)));
+            NNS_CUDA(cudaFuncSetAttribute(chorin_wave_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)WaveSmem<C>::SMEM_BYTES));
+        }
     }
     StreamArgs a{};
     a.g = h->g;
@@ -763,8 +1181,27 @@ int chorin_stream_step(nns_handle *h, const double *uc, const double *vc, const 
     a.sweeps = sweeps;
     a.nonfinite = h->d_nonfinite;
     a.prof = pl->d_prof;
+    a.trace = pl->d_trace;
     const int grid = count < pl->grid ? count : pl->grid;
-    chorin_stream_kernel<C><<<grid, NT_SOR + NT_ST, C::SMEM_BYTES, st>>>(a);
+    if (pl->wave) {
+        a.redo_count = pl->d_redo;
+        a.redo_list = pl->d_redo + 1;
+        a.pscr = pl->d_pscr;
+        for (int w = 0; w < NW_SOR; ++w) { a.wamin[w] = pl->wamin[w]; a.wrange[w] = pl->wrange[w]; }
+        a.rmax = pl->rmax;
+        NNS_CUDA(cudaMemsetAsync(pl->d_redo, 0, sizeof(int), st));
+        chorin_wave_kernel<C><<<grid, NT_SOR + NT_ST, WaveSmem<C>::SMEM_BYTES, st>>>(a);
+        NNS_CUDA(cudaGetLastError());
+        // re-run pass: members whose SOR loop stops before nit - 1 sweeps (none in the common case: the CTAs
+        // read an empty list and leave)
+        a.list = a.redo_list;
+        a.list_count = a.redo_count;
+        chorin_stream_kernel<C, true><<<grid, NT_SOR + NT_ST, C::SMEM_BYTES, st>>>(a);
+        NNS_CUDA(cudaGetLastError());
+        h->launches += 2;
+        return NNS_OK;
+    }
+    chorin_stream_kernel<C, false><<<grid, NT_SOR + NT_ST, C::SMEM_BYTES, st>>>(a);
     NNS_CUDA(cudaGetLastError());
     h->launches += 1;
     return NNS_OK;

@@ -2,6 +2,7 @@
 // microbenchmark (scripts/micro/sweep_bench.cu).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 namespace nns {
 
@@ -87,6 +88,71 @@ __device__ __forceinline__ void block_sweep(double (&P)[BR][BC], const double2 *
 #endif
     constexpr int NR = R1 - R0, ND = NR + BC - 1;
     double base[2][NR];
+#ifdef NNS_SOR_ROUNDS
+    // Source order = issue order wanted: the three-deep dependency chains of stage A (next diagonal) and stage B
+    // (this diagonal) are written out in rounds over the cells of a diagonal and interleaved round by round, so that
+    // neighbouring instructions are independent (in-order issue, 8-cycle DFMA latency).
+    {
+        double cpv[2][NR];
+        auto loadA = [&](int kd, double (&cp)[NR], double (&sv)[NR], double (&ev)[NR]) {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const int lj = kd - r, li = R0 + r;
+                if (lj >= 0 && lj < BC) {
+                    const int o = split_ord<BR, BC, RS>(li, lj);
+                    const double2 cc2 = Cme[(o >> 1) * NT_SOR];
+                    cp[r] = (o & 1) ? cc2.y : cc2.x;
+                    sv[r] = li < BR - 1 ? P[li + 1][lj] : h.hS[lj * NT_SOR];
+                    ev[r] = lj < BC - 1 ? P[li][lj + 1] : h.hE[li * NT_SOR];
+                }
+            }
+        };
+        double sv[NR], ev[NR], nv[NR], wv[NR], t[NR];
+        loadA(0, cpv[0], sv, ev);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) if (0 - r >= 0 && 0 - r < BC) base[0][r] = fma(k.ca, sv[r], fma(k.cb, ev[r], fma(k.cc, P[R0 + r][0 - r], -cpv[0][r])));
+#pragma unroll
+        for (int kd = 0; kd < ND; ++kd) {
+            const bool nxt = kd + 1 < ND;
+            if (nxt) loadA(kd + 1, cpv[(kd + 1) & 1], sv, ev);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const int lj = kd - r, li = R0 + r;
+                if (lj >= 0 && lj < BC) {
+                    nv[r] = li > 0 ? P[li - 1][lj] : h.hN[lj * NT_SOR];
+                    wv[r] = lj > 0 ? P[li][lj - 1] : h.hW[li * NT_SOR];
+                }
+            }
+            // round 1
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const int lj = kd - r, lja = kd + 1 - r;
+                if (lj >= 0 && lj < BC) t[r] = fma(k.cb, wv[r], base[kd & 1][r]);
+                if (nxt && lja >= 0 && lja < BC) base[(kd + 1) & 1][r] = fma(k.cc, P[R0 + r][lja], -cpv[(kd + 1) & 1][r]);
+            }
+            // round 2
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const int lj = kd - r, lja = kd + 1 - r;
+                if (lj >= 0 && lj < BC) t[r] = fma(k.ca, nv[r], t[r]);
+                if (nxt && lja >= 0 && lja < BC) base[(kd + 1) & 1][r] = fma(k.cb, ev[r], base[(kd + 1) & 1][r]);
+            }
+            // round 3
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const int lj = kd - r, li = R0 + r, lja = kd + 1 - r;
+                if (lj >= 0 && lj < BC) {
+                    if (TRACK == 1) mhi = max(mhi, (unsigned)__double2hiint(t[r]) & 0x7fffffffu);
+                    if (TRACK == 2) viol |= exceeds_bits(t[r], tolbits);
+                    P[li][lj] += t[r];
+                }
+                if (nxt && lja >= 0 && lja < BC) base[(kd + 1) & 1][r] = fma(k.ca, sv[r], base[(kd + 1) & 1][r]);
+            }
+        }
+        publish<BR, BC, R0, R1>(P, h);
+        return;
+    }
+#endif
     auto stageA = [&](int kd, double (&out)[NR]) {
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
@@ -153,6 +219,123 @@ __device__ __forceinline__ void block_sweep(double (&P)[BR][BC], const double2 *
 #if !defined(NNS_ABL_NOPUBLISH) && !defined(NNS_SOR_PUBLISH_EARLY)
     publish<BR, BC, R0, R1>(P, h);
 #endif
+}
+
+// ----------------------------------------------------------------------------------------------
+// Tensor Memory as a thread-private scratchpad (chorin_wave_kernel of chorin_fd_stream.cu): the right-hand
+// side C' of a thread lives in the thread's own TMEM lane (tcgen05.ld/st shape 32x32b: thread i of the warp
+// accesses lane 32*(warp%4)+i, consecutive 32-bit columns), in the same 16-byte chunks and the same
+// consumption order as the shared-memory layout above.  Measured on B200 (scripts/micro/tmem_bench.cu): x4
+// loads sustain ~50 B/clk per SM sub-partition on a pipe of their own, latency ~35 cycles, so the sweeps no
+// longer compete with the stencil role for the single shared-memory pipe of the SM.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tm_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+// wait for every outstanding tcgen05.ld of the thread; the registers are tied to the statement so that the
+// compiler cannot move a use in front of the wait
+__device__ __forceinline__ void tm_wait_ld(uint32_t (&r)[4]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3])::"memory");
+}
+__device__ __forceinline__ void tm_tie(uint32_t (&r)[4]) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3])::"memory");
+}
+
+// number of cells of an NR x BC sub-block on anti-diagonals < t
+template <int NR, int BC>
+__host__ __device__ constexpr int diag_cum(int t) {
+    int o = 0;
+    for (int d = 0; d < t; ++d) {
+        const int lo = d - (BC - 1) > 0 ? d - (BC - 1) : 0, hi = d < NR - 1 ? d : NR - 1;
+        if (hi >= lo) o += hi - lo + 1;
+    }
+    return o;
+}
+
+// block_sweep with the right-hand side in Tensor Memory and WARP-UNIFORM control flow (tcgen05.ld is a
+// warp-collective instruction): every lane executes the sweep, lanes outside the wavefront band (`act`
+// false) compute on whatever their registers hold and commit nothing.  tmc: TMEM address of chunk 0 of the
+// member's C' buffer of this thread.  pubTL false: the top row / left column are not published (last sweep
+// of a member: nobody reads them, and the neighbour may already have deposited the next member's start
+// values in those slots).  The chunk loads run one anti-diagonal ahead of their use.
+template <int BR, int BC, int RS, int R0, int R1>
+__device__ __forceinline__ void block_sweep_tm(double (&P)[BR][BC], uint32_t tmc, const SHalo<BR, BC> &h, const Coef &k,
+                                               bool act, bool pubTL, unsigned &mhi) {
+    constexpr int NR = R1 - R0, ND = NR + BC - 1;
+    constexpr int OB = R0 == 0 ? 0 : RS * BC;                  // first cell (consumption order) of this sub-block
+    constexpr int CLO = OB >> 1, CHI = (OB + NR * BC - 1) >> 1, NCQ = CHI - CLO + 1;
+    uint32_t cq[NCQ][4];
+    // last chunk needed by the cells of diagonal kd
+    auto chi = [](int kd) { return (OB + diag_cum<NR, BC>(kd + 1) - 1) >> 1; };
+    auto issue = [&](int from, int to) {       // chunks (from, to]
+#pragma unroll
+        for (int c = CLO; c <= CHI; ++c)
+            if (c > from && c <= to) tm_ld4(tmc + 4 * c, cq[c - CLO]);
+    };
+    auto wait = [&](int from, int to) {
+        bool first = true;
+#pragma unroll
+        for (int c = CLO; c <= CHI; ++c)
+            if (c > from && c <= to) {
+                if (first) tm_wait_ld(cq[c - CLO]);
+                else tm_tie(cq[c - CLO]);
+                first = false;
+            }
+    };
+    const double actf = act ? 1.0 : 0.0;
+    double base[2][NR];
+    auto stageA = [&](int kd, double (&out)[NR]) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int lj = kd - r, li = R0 + r;
+            if (lj >= 0 && lj < BC) {
+                const int o = split_ord<BR, BC, RS>(li, lj);
+                const uint32_t(&c4)[4] = cq[(o >> 1) - CLO];
+                const double cp = (o & 1) ? __hiloint2double((int)c4[3], (int)c4[2]) : __hiloint2double((int)c4[1], (int)c4[0]);
+                const double s = li < BR - 1 ? P[li + 1][lj] : h.hS[lj * NT_SOR];
+                const double e = lj < BC - 1 ? P[li][lj + 1] : h.hE[li * NT_SOR];
+                out[r] = fma(k.ca, s, fma(k.cb, e, fma(k.cc, P[li][lj], -cp)));
+            }
+        }
+    };
+    issue(CLO - 1, chi(1));
+    wait(CLO - 1, chi(1));
+    if (ND > 2) issue(chi(1), chi(2));
+    stageA(0, base[0]);
+#pragma unroll
+    for (int kd = 0; kd < ND; ++kd) {
+        if (kd + 1 < ND) {
+            if (kd >= 1) wait(chi(kd), chi(kd + 1));
+            if (kd >= 1 && kd + 2 < ND) issue(chi(kd + 1), chi(kd + 2));
+            stageA(kd + 1, base[(kd + 1) & 1]);
+        }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int lj = kd - r, li = R0 + r;
+            if (lj >= 0 && lj < BC) {
+                const double n = li > 0 ? P[li - 1][lj] : h.hN[lj * NT_SOR];
+                const double w = lj > 0 ? P[li][lj - 1] : h.hW[li * NT_SOR];
+                const double d = fma(k.ca, n, fma(k.cb, w, base[kd & 1][r]));
+                mhi = max(mhi, (unsigned)__double2hiint(d) & 0x7fffffffu);
+                // p += d for the lanes inside the band, p unchanged (+ 0 * d) for the others: one DFMA, like the
+                // DADD of the legacy sweep and bit-identical to it for actf == 1 (a select would cost two extra
+                // instructions per cell)
+                P[li][lj] = fma(d, actf, P[li][lj]);
+            }
+        }
+    }
+    const bool pT = h.pubT && act && pubTL, pB = h.pubB && act, pL = h.pubL && act && pubTL, pR = h.pubR && act;
+#pragma unroll
+    for (int lj = 0; lj < BC; ++lj) {
+        if (R0 == 0 && pT) h.Hme[lj * NT_SOR] = P[0][lj];
+        if (R1 == BR && pB) h.Hme[(BC + lj) * NT_SOR] = P[BR - 1][lj];
+    }
+#pragma unroll
+    for (int li = R0; li < R1; ++li) {
+        if (pL) h.Hme[(2 * BC + li) * NT_SOR] = P[li][0];
+        if (pR) h.Hme[(2 * BC + BR + li) * NT_SOR] = P[li][BC - 1];
+    }
 }
 
 }  // namespace nns
