@@ -61,7 +61,12 @@ __host__ __device__ constexpr int diag_ord(int li, int lj) {
 // [RS, BR): the cells of the top sub-block in its diagonal order, then those of the bottom one.
 template <int BR, int BC, int RS>
 __host__ __device__ constexpr int split_ord(int li, int lj) {
-    return li < RS ? diag_ord<RS, BC>(li, lj) : RS * BC + diag_ord<BR - RS, BC>(li - RS, lj);
+    if (RS < 0) {       // three sub-blocks of -RS rows each (BR == -3 * RS)
+        constexpr int H = RS < 0 ? -RS : 1;
+        const int kb = li / H;
+        return kb * H * BC + diag_ord<H, BC>(li - kb * H, lj);
+    }
+    return li < RS ? diag_ord<(RS > 0 ? RS : 1), BC>(li, lj) : RS * BC + diag_ord<(RS > 0 ? BR - RS : 1), BC>(li - RS, lj);
 }
 
 // One sweep over rows [R0, R1) of the thread's own BR x BC block (the block is swept as two sub-blocks
@@ -88,71 +93,6 @@ __device__ __forceinline__ void block_sweep(double (&P)[BR][BC], const double2 *
 #endif
     constexpr int NR = R1 - R0, ND = NR + BC - 1;
     double base[2][NR];
-#ifdef NNS_SOR_ROUNDS
-    // Source order = issue order wanted: the three-deep dependency chains of stage A (next diagonal) and stage B
-    // (this diagonal) are written out in rounds over the cells of a diagonal and interleaved round by round, so that
-    // neighbouring instructions are independent (in-order issue, 8-cycle DFMA latency).
-    {
-        double cpv[2][NR];
-        auto loadA = [&](int kd, double (&cp)[NR], double (&sv)[NR], double (&ev)[NR]) {
-#pragma unroll
-            for (int r = 0; r < NR; ++r) {
-                const int lj = kd - r, li = R0 + r;
-                if (lj >= 0 && lj < BC) {
-                    const int o = split_ord<BR, BC, RS>(li, lj);
-                    const double2 cc2 = Cme[(o >> 1) * NT_SOR];
-                    cp[r] = (o & 1) ? cc2.y : cc2.x;
-                    sv[r] = li < BR - 1 ? P[li + 1][lj] : h.hS[lj * NT_SOR];
-                    ev[r] = lj < BC - 1 ? P[li][lj + 1] : h.hE[li * NT_SOR];
-                }
-            }
-        };
-        double sv[NR], ev[NR], nv[NR], wv[NR], t[NR];
-        loadA(0, cpv[0], sv, ev);
-#pragma unroll
-        for (int r = 0; r < NR; ++r) if (0 - r >= 0 && 0 - r < BC) base[0][r] = fma(k.ca, sv[r], fma(k.cb, ev[r], fma(k.cc, P[R0 + r][0 - r], -cpv[0][r])));
-#pragma unroll
-        for (int kd = 0; kd < ND; ++kd) {
-            const bool nxt = kd + 1 < ND;
-            if (nxt) loadA(kd + 1, cpv[(kd + 1) & 1], sv, ev);
-#pragma unroll
-            for (int r = 0; r < NR; ++r) {
-                const int lj = kd - r, li = R0 + r;
-                if (lj >= 0 && lj < BC) {
-                    nv[r] = li > 0 ? P[li - 1][lj] : h.hN[lj * NT_SOR];
-                    wv[r] = lj > 0 ? P[li][lj - 1] : h.hW[li * NT_SOR];
-                }
-            }
-            // round 1
-#pragma unroll
-            for (int r = 0; r < NR; ++r) {
-                const int lj = kd - r, lja = kd + 1 - r;
-                if (lj >= 0 && lj < BC) t[r] = fma(k.cb, wv[r], base[kd & 1][r]);
-                if (nxt && lja >= 0 && lja < BC) base[(kd + 1) & 1][r] = fma(k.cc, P[R0 + r][lja], -cpv[(kd + 1) & 1][r]);
-            }
-            // round 2
-#pragma unroll
-            for (int r = 0; r < NR; ++r) {
-                const int lj = kd - r, lja = kd + 1 - r;
-                if (lj >= 0 && lj < BC) t[r] = fma(k.ca, nv[r], t[r]);
-                if (nxt && lja >= 0 && lja < BC) base[(kd + 1) & 1][r] = fma(k.cb, ev[r], base[(kd + 1) & 1][r]);
-            }
-            // round 3
-#pragma unroll
-            for (int r = 0; r < NR; ++r) {
-                const int lj = kd - r, li = R0 + r, lja = kd + 1 - r;
-                if (lj >= 0 && lj < BC) {
-                    if (TRACK == 1) mhi = max(mhi, (unsigned)__double2hiint(t[r]) & 0x7fffffffu);
-                    if (TRACK == 2) viol |= exceeds_bits(t[r], tolbits);
-                    P[li][lj] += t[r];
-                }
-                if (nxt && lja >= 0 && lja < BC) base[(kd + 1) & 1][r] = fma(k.ca, sv[r], base[(kd + 1) & 1][r]);
-            }
-        }
-        publish<BR, BC, R0, R1>(P, h);
-        return;
-    }
-#endif
     auto stageA = [&](int kd, double (&out)[NR]) {
 #pragma unroll
         for (int r = 0; r < NR; ++r) {

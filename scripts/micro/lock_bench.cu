@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(384, 1) lock_kernel(const SBlock *desc, long l
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_SOR));
         const int w = tid >> 5;
         const uint32_t tm_mine = tmem + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(256 * (w >> 2));
-        if (TM) {
+        if (TM || PMAP == 6) {
             for (int c = 0; c < 32; c += 4) {
                 double2 v[4];
                 for (int e = 0; e < 4; ++e) v[e] = make_double2(1e-3 * ((c + e) * 7 + tid % 13), 2e-3 * ((c + e) * 5 + tid % 11));
@@ -68,6 +68,16 @@ __global__ void __launch_bounds__(384, 1) lock_kernel(const SBlock *desc, long l
                 if (TM) {
                     if (top) block_sweep_tm<BR, BC, RS, 0, RS>(P, tm_mine, h, k, owner, true, mhi);
                     else block_sweep_tm<BR, BC, RS, RS, BR>(P, tm_mine, h, k, owner, true, mhi);
+                } else if (PMAP == 6) {      // hybrid: top sub-block's C' from shared memory, bottom sub-block's from Tensor Memory
+                    if (top) block_sweep<BR, BC, RS, 0, RS, 1>(P, Cs + tid, h, k, tolbits, mhi, v);
+                    else block_sweep_tm<BR, BC, RS, RS, BR>(P, tm_mine, h, k, owner, true, mhi);
+                } else if (PMAP == 5) {      // three sub-blocks of 3 rows: even stages sweep sub-blocks 0 and 2, odd stages sub-block 1
+                    if (top) {
+                        block_sweep<BR, BC, -3, 0, 3, 1>(P, Cs + tid, h, k, tolbits, mhi, v);
+                        block_sweep<BR, BC, -3, 6, 9, 1>(P, Cs + tid, h, k, tolbits, mhi, v);
+                    } else {
+                        block_sweep<BR, BC, -3, 3, 6, 1>(P, Cs + tid, h, k, tolbits, mhi, v);
+                    }
                 } else if (PMAP == 2) {      // same sub-block every stage, two distinct copies of the code (TRACK 1 / TRACK 2)
                     if (top) block_sweep<BR, BC, RS, 0, RS, 1>(P, Cs + tid, h, k, tolbits, mhi, v);
                     else block_sweep<BR, BC, RS, 0, RS, 2>(P, Cs + tid, h, k, tolbits, mhi, v);
@@ -133,6 +143,13 @@ int main() {
     run<false, 1, 1>(d_desc, cyc, 8, "smem C', barrier, same kind per SMSP");
     run<true, 0, 1>(d_desc, cyc, 8, "TMEM C', free running, same kind per SMSP");
     run<true, 1, 1>(d_desc, cyc, 8, "TMEM C', barrier, same kind per SMSP");
+    run<false, 0, 6>(d_desc, cyc, 8, "hybrid top smem / bottom TMEM, free running");
+    run<false, 1, 6>(d_desc, cyc, 8, "hybrid top smem / bottom TMEM, barrier");
+    run<false, 0, 6>(d_desc, cyc, 4, "hybrid, free running, 1 warp/SMSP");
+    run<false, 0, 5>(d_desc, cyc, 8, "three sub-blocks, free running");
+    run<false, 1, 5>(d_desc, cyc, 8, "three sub-blocks, barrier per stage");
+    run<false, 0, 5>(d_desc, cyc, 4, "three sub-blocks, free running, 1 warp/SMSP");
+    run<false, 1, 5>(d_desc, cyc, 4, "three sub-blocks, barrier, 1 warp/SMSP");
     run<false, 0, 3>(d_desc, cyc, 4, "top only, one code copy, 1 warp/SMSP");
     run<false, 0, 4>(d_desc, cyc, 4, "top only (exact test), one copy, 1 warp/SMSP");
     run<false, 0, 2>(d_desc, cyc, 4, "top only, two code copies, 1 warp/SMSP");

@@ -135,3 +135,60 @@ def test_stream_equals_member_kernel(monkeypatch):
     assert int(a[3].min()) < 49
     for x, y in zip(a[:3], b[:3]):
         assert float((x - y).norm() / y.norm()) <= 1e-13
+
+
+def _run_mode(monkeypatch, mode, B, steps, **kw):
+    import torch
+    from nns_b200.ensemble import cavity_bcs, cavity_ensemble_params
+    monkeypatch.delenv("NNS_CHIP_MODE", raising=False)
+    monkeypatch.setenv("NNS_STREAM_MODE", mode)
+    lid, nu = cavity_ensemble_params(B, seed=11)
+    if "lid" in kw:
+        lid = kw.pop("lid")
+        nu = np.full(len(lid), 0.1)
+    dx = dy = 2. / (NX - 1)
+    u_bc, v_bc, p_bc = cavity_bcs(dx, dy)
+    ens = _ens(B, u_bc, v_bc, p_bc, nu, lid, **kw)
+    ens.init_variables()
+    sw = []
+    for _ in range(steps):
+        ens.step()
+        sw.append(ens.sweeps.clone())
+    return ens.u.clone(), ens.v.clone(), ens.p.clone(), torch.stack(sw), ens.launches
+
+
+def test_wave_kernel_is_bit_identical_to_member_at_a_time_kernel(monkeypatch):
+    """The wave kernel (continuous SOR wavefront over the members of a CTA, right-hand side in Tensor Memory,
+    NNS_STREAM_MODE=wave) executes the same operations per cell in the same order as the member-at-a-time
+    kernel: u, v, p bit-identical and sweep counts equal, with several members per CTA and a ragged tail."""
+    import torch
+    a = _run_mode(monkeypatch, "wave", 333, 3)
+    b = _run_mode(monkeypatch, "legacy", 333, 3)
+    assert a[4] > b[4]                       # the wave path really ran (it adds the re-run launch)
+    assert torch.equal(a[3], b[3]) and int(a[3].min()) == 49
+    for x, y in zip(a[:3], b[:3]):
+        assert torch.equal(x, y)
+
+
+def test_wave_kernel_early_exit_members_take_the_rerun_pass(oracle_fd, monkeypatch):
+    """Members whose SOR loop stops before nit - 1 sweeps are detected from the exit flags of the pipelined
+    pass, left untouched and re-run by the member-at-a-time kernel with the exact sweep count: sweep counts
+    and fields vs the oracle, next to members that run all 49 sweeps in the same launch."""
+    lid = np.array([3e-7, 1e-6, 2e-6, 1e-5, 1e-4, 1.0])
+    u, v, p, sw, _ = _run_mode(monkeypatch, "wave", len(lid), 3, lid=lid)
+    from nns_b200.ensemble import cavity_bcs
+    dx = dy = 2. / (NX - 1)
+    u_bc, v_bc, p_bc = cavity_bcs(dx, dy)
+    z = np.zeros((NX, NY))
+    seen = set()
+    for b in range(len(lid)):
+        ub = _bc_tuples(u_bc)
+        ub[1] = ("right", "dirichlet", float(lid[b]))
+        ou, ov, op, osw = oracle_fd.chorin_simulate(z, z, z, ub, _bc_tuples(v_bc), _bc_tuples(p_bc), nt=3, nit=50,
+                                                    dt=2e-4, rho=1, nu=0.1, beta=1.25)
+        assert list(sw[:, b].cpu().numpy()) == list(osw)
+        seen.update(int(s) for s in osw)
+        assert rel_l2(u[b].cpu().numpy(), ou[-1]) <= TOL
+        assert rel_l2(v[b].cpu().numpy(), ov[-1]) <= TOL
+        assert rel_l2(p[b].cpu().numpy(), op[-1]) <= TOL
+    assert min(seen) < 49 and max(seen) == 49, seen
