@@ -222,6 +222,24 @@ int32_t nns_chorin_fd_slab_step(nns_handle *h, const double *u, const double *v,
 /* Device time (CUDA events) of the SOR tick loop of the last step and its number of ticks (= sweep-kernel launches). */
 int32_t nns_slab_last_timing(nns_handle *h, float *sor_ms, int32_t *ticks);
 
+/* ---- trajectory sink (the interface between the time-step path and the rest of the reference) ---- */
+
+/* Block means of device trajectories, replaces utils.spatial_coarsen (src/utils.py:13-60) for the u, v, p
+ * sequences: inputs [frames][nx][ny] float64 (frames = members * nt), outputs [frames][nx/agg_x][ny/agg_y]
+ * float64.  Every block mean is summed in NumPy's pairwise order and divided once, i.e. bit-identical to
+ * np.mean over the flattened block; like the reference loop (utils.py:49) only the first ny // agg_x output
+ * columns are written, the others are zero.  nx % agg_x, ny % agg_y != 0 -> NNS_ERR_INVALID (AssertionError
+ * in the reference), ny // agg_x > ny // agg_y -> NNS_ERR_INVALID (IndexError there). */
+int32_t nns_traj_coarsen(const double *u, const double *v, const double *p, int64_t frames, int32_t nx, int32_t ny,
+                         int32_t agg_x, int32_t agg_y, double *u_out, double *v_out, double *p_out, void *stream);
+
+/* The float32 observation tensor the neural scripts build from a data file
+ * (src/neural_spectral/rnn.py:77-82, spectral_ode.py:158-163: stack([u, v, p]).permute(1, 0, 2, 3) of the
+ * .float() fields): obs_out [frames][3][nx/agg_x][ny/agg_y] float32, optionally of the coarsened fields
+ * (agg_x = agg_y = 1: plain conversion). */
+int32_t nns_traj_observations(const double *u, const double *v, const double *p, int64_t frames, int32_t nx, int32_t ny,
+                              int32_t agg_x, int32_t agg_y, float *obs_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

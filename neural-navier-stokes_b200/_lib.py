@@ -61,6 +61,8 @@ _PROTOS = {
     "nns_slab_ipc_connect": (_i32, [_vp, _vp, _vp]),
     "nns_chorin_fd_slab_step": (_i32, [_vp] * 10),
     "nns_slab_last_timing": (_i32, [_vp, C.POINTER(C.c_float), C.POINTER(_i32)]),
+    "nns_traj_coarsen": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "nns_traj_observations": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "nns_spectral_set_operators": (_i32, [_vp, C.POINTER(_vp), _i32]),
     "nns_spectral_predictor": (_i32, [_vp] * 8),
     "nns_spectral_correct": (_i32, [_vp] * 9),

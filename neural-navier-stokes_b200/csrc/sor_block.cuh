@@ -161,6 +161,77 @@ __device__ __forceinline__ void block_sweep(double (&P)[BR][BC], const double2 *
 #endif
 }
 
+// number of cells of an NR x BC sub-block on anti-diagonals < t
+template <int NR, int BC>
+__host__ __device__ constexpr int diag_cum(int t) {
+    int o = 0;
+    for (int d = 0; d < t; ++d) {
+        const int lo = d - (BC - 1) > 0 ? d - (BC - 1) : 0, hi = d < NR - 1 ? d : NR - 1;
+        if (hi >= lo) o += hi - lo + 1;
+    }
+    return o;
+}
+
+// block_sweep with the loads of the right-hand side issued PFD anti-diagonals ahead of their use (explicit chunk
+// schedule, volatile loads).  With C' re-read from shared memory in every sweep the plain block_sweep is bound by
+// the exposed load latency at every diagonal step (890 cycles per 31.5-cell sweep against 536 when C' sits in
+// registers, scripts/micro/lock_bench.cu): there are no spare registers for the compiler to hoist the loads.
+__device__ __forceinline__ double2 lds_f64x2_volatile(const double2 *p) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+}
+template <int BR, int BC, int RS, int R0, int R1, int TRACK, int PFD>
+__device__ __forceinline__ void block_sweep_pf(double (&P)[BR][BC], const double2 *__restrict__ Cme, const SHalo<BR, BC> &h,
+                                               const Coef &k, unsigned long long tolbits, unsigned &mhi, bool &viol) {
+    constexpr int NR = R1 - R0, ND = NR + BC - 1;
+    constexpr int OB = R0 == 0 ? 0 : RS * BC;
+    constexpr int CLO = OB >> 1, CHI = (OB + NR * BC - 1) >> 1, NCQ = CHI - CLO + 1;
+    double2 cq[NCQ];
+    auto chi = [](int kd) { return kd < 0 ? CLO - 1 : kd >= ND ? CHI : (OB + diag_cum<NR, BC>(kd + 1) - 1) >> 1; };
+    auto issue = [&](int from, int to) {
+#pragma unroll
+        for (int c = CLO; c <= CHI; ++c)
+            if (c > from && c <= to) cq[c - CLO] = lds_f64x2_volatile(Cme + c * NT_SOR);
+    };
+    double base[2][NR];
+    auto stageA = [&](int kd, double (&out)[NR]) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int lj = kd - r, li = R0 + r;
+            if (lj >= 0 && lj < BC) {
+                const int o = split_ord<BR, BC, RS>(li, lj);
+                const double cp = (o & 1) ? cq[(o >> 1) - CLO].y : cq[(o >> 1) - CLO].x;
+                const double s = li < BR - 1 ? P[li + 1][lj] : h.hS[lj * NT_SOR];
+                const double e = lj < BC - 1 ? P[li][lj + 1] : h.hE[li * NT_SOR];
+                out[r] = fma(k.ca, s, fma(k.cb, e, fma(k.cc, P[li][lj], -cp)));
+            }
+        }
+    };
+    issue(CLO - 1, chi(PFD));                  // diagonals 0 .. PFD
+    stageA(0, base[0]);
+#pragma unroll
+    for (int kd = 0; kd < ND; ++kd) {
+        if (kd + 1 < ND) {
+            issue(chi(kd + PFD), chi(kd + 1 + PFD));
+            stageA(kd + 1, base[(kd + 1) & 1]);
+        }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int lj = kd - r, li = R0 + r;
+            if (lj >= 0 && lj < BC) {
+                const double n = li > 0 ? P[li - 1][lj] : h.hN[lj * NT_SOR];
+                const double w = lj > 0 ? P[li][lj - 1] : h.hW[li * NT_SOR];
+                const double d = fma(k.ca, n, fma(k.cb, w, base[kd & 1][r]));
+                if (TRACK == 1) mhi = max(mhi, (unsigned)__double2hiint(d) & 0x7fffffffu);
+                if (TRACK == 2) viol |= exceeds_bits(d, tolbits);
+                P[li][lj] += d;
+            }
+        }
+    }
+    publish<BR, BC, R0, R1>(P, h);
+}
+
 // ----------------------------------------------------------------------------------------------
 // Tensor Memory as a thread-private scratchpad (chorin_wave_kernel of chorin_fd_stream.cu): the right-hand
 // side C' of a thread lives in the thread's own TMEM lane (tcgen05.ld/st shape 32x32b: thread i of the warp
@@ -182,16 +253,6 @@ __device__ __forceinline__ void tm_tie(uint32_t (&r)[4]) {
     asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3])::"memory");
 }
 
-// number of cells of an NR x BC sub-block on anti-diagonals < t
-template <int NR, int BC>
-__host__ __device__ constexpr int diag_cum(int t) {
-    int o = 0;
-    for (int d = 0; d < t; ++d) {
-        const int lo = d - (BC - 1) > 0 ? d - (BC - 1) : 0, hi = d < NR - 1 ? d : NR - 1;
-        if (hi >= lo) o += hi - lo + 1;
-    }
-    return o;
-}
 
 // block_sweep with the right-hand side in Tensor Memory and WARP-UNIFORM control flow (tcgen05.ld is a
 // warp-collective instruction): every lane executes the sweep, lanes outside the wavefront band (`act`

@@ -68,6 +68,9 @@ __global__ void __launch_bounds__(384, 1) lock_kernel(const SBlock *desc, long l
                 if (TM) {
                     if (top) block_sweep_tm<BR, BC, RS, 0, RS>(P, tm_mine, h, k, owner, true, mhi);
                     else block_sweep_tm<BR, BC, RS, RS, BR>(P, tm_mine, h, k, owner, true, mhi);
+                } else if (PMAP >= 10) {     // explicit C' prefetch PMAP - 10 diagonals ahead
+                    if (top) block_sweep_pf<BR, BC, RS, 0, RS, 1, PMAP - 10>(P, Cs + tid, h, k, tolbits, mhi, v);
+                    else block_sweep_pf<BR, BC, RS, RS, BR, 1, PMAP - 10>(P, Cs + tid, h, k, tolbits, mhi, v);
                 } else if (PMAP == 6) {      // hybrid: top sub-block's C' from shared memory, bottom sub-block's from Tensor Memory
                     if (top) block_sweep<BR, BC, RS, 0, RS, 1>(P, Cs + tid, h, k, tolbits, mhi, v);
                     else block_sweep_tm<BR, BC, RS, RS, BR>(P, tm_mine, h, k, owner, true, mhi);
@@ -143,6 +146,14 @@ int main() {
     run<false, 1, 1>(d_desc, cyc, 8, "smem C', barrier, same kind per SMSP");
     run<true, 0, 1>(d_desc, cyc, 8, "TMEM C', free running, same kind per SMSP");
     run<true, 1, 1>(d_desc, cyc, 8, "TMEM C', barrier, same kind per SMSP");
+    run<false, 0, 11>(d_desc, cyc, 4, "C' prefetch 1 diagonal ahead, 1 warp/SMSP");
+    run<false, 0, 12>(d_desc, cyc, 4, "C' prefetch 2 diagonals ahead, 1 warp/SMSP");
+    run<false, 0, 13>(d_desc, cyc, 4, "C' prefetch 3 diagonals ahead, 1 warp/SMSP");
+    run<false, 0, 11>(d_desc, cyc, 8, "C' prefetch 1 diagonal ahead, free running");
+    run<false, 0, 12>(d_desc, cyc, 8, "C' prefetch 2 diagonals ahead, free running");
+    run<false, 0, 13>(d_desc, cyc, 8, "C' prefetch 3 diagonals ahead, free running");
+    run<false, 1, 12>(d_desc, cyc, 8, "C' prefetch 2 diagonals ahead, barrier");
+    run<false, 1, 13>(d_desc, cyc, 8, "C' prefetch 3 diagonals ahead, barrier");
     run<false, 0, 6>(d_desc, cyc, 8, "hybrid top smem / bottom TMEM, free running");
     run<false, 1, 6>(d_desc, cyc, 8, "hybrid top smem / bottom TMEM, barrier");
     run<false, 0, 6>(d_desc, cyc, 4, "hybrid, free running, 1 warp/SMSP");
