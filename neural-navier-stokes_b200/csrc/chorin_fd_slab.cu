@@ -218,6 +218,12 @@ struct SweepArgs {
     double *p;
     const double *cp;
     int *flags;        // [cap] set to 1 when sweep s still violates the exit test; null = no tracking
+    // peer-memory exchange fused into the sweep (null = the halo rows of p are maintained by the host loop):
+    // the rows just outside the slab are READ from this rank's mailbox, and the slab's first / last row are also
+    // STORED into the neighbours' mailboxes (NVLink) by the tiles that update them.
+    const double *halo_top, *halo_bot;
+    double *push_up, *push_dn;
+    int first_row, last_row;      // global indices of the slab's first / last owned row
 };
 
 // 4 consecutive doubles of a row: one 256-bit access when the address is 32-byte aligned (VEC), else scalars
@@ -272,6 +278,12 @@ __global__ void __launch_bounds__(128) slab_sweep_kernel(const SweepArgs a, int 
     const double ca = g.beta * dy2 / den, cb = g.beta * dx2 / den, mbeta = -g.beta, tol = g.tol;
     double *P = a.p;
     const double *CP = a.cp;
+    // row i of p for reading: the neighbour's row in the mailbox if i lies just outside the slab
+    auto rowp = [&](int i) -> const double * {
+        if (a.halo_top && i == a.first_row - 1) return a.halo_top;
+        if (a.halo_bot && i == a.last_row + 1) return a.halo_bot;
+        return P + g.v.at(i, 0);
+    };
 
     // Software pipeline: the operands of row k are loaded PF steps before they are used, into a register ring
     // indexed by the step number (tau mod PF is the same for the load and the use of a row on every lane).
@@ -294,7 +306,7 @@ __global__ void __launch_bounds__(128) slab_sweep_kernel(const SweepArgs a, int 
     auto prefetch = [&](int k, int slot) {        // operands of tile row k into ring slot `slot`
         if (has && k >= 0 && k < nr) {
             const size_t q = g.v.at(i0 + k, c0);
-            load4<VEC>(P + q + ny, nin, qs[slot]);
+            load4<VEC>(rowp(i0 + k + 1) + c0, nin, qs[slot]);
             load4<VEC>(CP + q, nin, qc[slot]);
             if (east_load) qe[slot] = P[q + LC];
             if (lane == 0 && c0 > 0) qw[slot] = P[q - 1];
@@ -304,7 +316,7 @@ __global__ void __launch_bounds__(128) slab_sweep_kernel(const SweepArgs a, int 
     // would stall the WHOLE warp at the next use of pc / pn: the scoreboard tracks registers per warp)
     if (has) {
         const size_t q = g.v.at(i0, c0);
-        load4<VEC>(P + q - ny, nin, pn);
+        load4<VEC>(rowp(i0 - 1) + c0, nin, pn);
         load4<VEC>(P + q, nin, pc);
     }
 #pragma unroll
@@ -340,6 +352,8 @@ __global__ void __launch_bounds__(128) slab_sweep_kernel(const SweepArgs a, int 
                     pc[jj] = qs[dd][jj];
                 }
                 store4<VEC>(P + q, nin, out);
+                if (a.push_up && i0 + k == a.first_row) store4<VEC>(a.push_up + c0, nin, out);
+                if (a.push_dn && i0 + k == a.last_row) store4<VEC>(a.push_dn + c0, nin, out);
                 wlast = w;
             }
             prefetch(k + PF, dd);      // refill the slot just consumed with the row PF steps ahead
@@ -394,6 +408,13 @@ __global__ void __launch_bounds__(1024) slab_push_row_kernel(const double *__res
     if (threadIdx.x == 0) *flag = seq;
 }
 
+// Raise the neighbours' flags after the sweep kernel of a tick (stream order: its remote stores are complete).
+__global__ void slab_flag_kernel(volatile unsigned *up, volatile unsigned *dn, unsigned seq) {
+    __threadfence_system();
+    if (up) *up = seq;
+    if (dn) *dn = seq;
+}
+
 int launch_sweep(nns_handle *h, SlabState *S, SweepArgs a, int Ia, int Ib, int T, cudaStream_t st) {
     if (Ib <= Ia) return NNS_OK;
     const int dmin = T - 2 * (a.cap - 1), dmax = T;
@@ -422,53 +443,58 @@ int run_sweeps(nns_handle *h, SlabState *S, const SlabGeom &g, double *p, int ca
         NNS_CUDA(cudaGetLastError());
         return NNS_OK;
     }
-    // Peer-memory exchange.  Per tick, in stream order: (1) wait for the neighbours' rows of the previous tick
-    // (stream memory operation on this rank's mailbox flag) and copy them into the halo rows, (2) sweep the
-    // tiles of the tick, (3) push the fresh boundary rows into the neighbours' mailboxes over NVLink and raise
-    // their flags.  No NCCL kernel and no host synchronisation inside the tick loop.
+    // Peer-memory exchange fused into the sweep kernel.  The mailbox holds ONE image of each neighbour's boundary
+    // row; the tiles of a tick that update the slab's first / last row store their chunks into the neighbours'
+    // mailboxes as well (NVLink stores), and the sweep kernel reads the rows just outside the slab from this
+    // rank's mailbox.  Per tick, in stream order: wait until both neighbours have finished the previous tick
+    // (stream memory operations on this rank's flags), sweep, raise the neighbours' flags.  A rank therefore runs
+    // at most concurrently with its neighbours' SAME tick, and within one tick the row segments a rank writes
+    // (tiles J with J = T - I - 2s) and the segments its neighbour reads have opposite parities of J: no chunk is
+    // read and written in the same tick, so a single image per row suffices.  No NCCL kernel, no copy kernel and
+    // no host synchronisation inside the tick loop.
     const bool up = S->rank > 0, dn = S->rank < S->nranks - 1;
     double *top_halo = p, *first = p + ny, *last = p + (size_t)S->nrows * ny, *bot_halo = p + (size_t)(S->nrows + 1) * ny;
-    for (int T = 0; T <= Tmax; ++T) {
-        const unsigned prev = S->seq;           // sequence number of the previous tick's rows
-        const unsigned cur = ++S->seq;
-        const int rb = prev & 1, wb = cur & 1;
-        if (T > 0) {
-            if (up) {
-                if (S->StreamWaitValue32((CUstream)st, (CUdeviceptr)(S->d_box + box_flag_off(0, ny)), prev, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) { set_error("cuStreamWaitValue32 failed"); return NNS_ERR_CUDA; }
-                NNS_CUDA(cudaMemcpyAsync(top_halo, S->d_box + box_row_off(0, rb, ny), sizeof(double) * ny, cudaMemcpyDeviceToDevice, st));
-            }
-            if (dn) {
-                if (S->StreamWaitValue32((CUstream)st, (CUdeviceptr)(S->d_box + box_flag_off(1, ny)), prev, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) { set_error("cuStreamWaitValue32 failed"); return NNS_ERR_CUDA; }
-                NNS_CUDA(cudaMemcpyAsync(bot_halo, S->d_box + box_row_off(1, rb, ny), sizeof(double) * ny, cudaMemcpyDeviceToDevice, st));
-            }
-        }
-        // One launch for all tile rows of the tick (a tile-sweep is one warp walking 128 + 31 dependent steps, so a
-        // separate launch for the tile rows next to a neighbour costs a full tile latency per tick: measured
-        // slower), then the fresh boundary rows go to the neighbours' mailboxes.
-        if ((rc = launch_sweep(h, S, a, S->I0, S->I1, T, st))) return rc;
-        if (up) {       // my first row is the "south, previous sweep" operand of the rank above: its mailbox dir 1
-            slab_push_row_kernel<<<1, 1024, 0, st>>>(first, reinterpret_cast<double *>(S->peer_box[0] + box_row_off(1, wb, ny)), ny,
-                                                     reinterpret_cast<volatile unsigned *>(S->peer_box[0] + box_flag_off(1, ny)), cur);
-            h->launches += 1;
-        }
-        if (dn) {       // my last row is the "north, same sweep" operand of the rank below: its mailbox dir 0
-            slab_push_row_kernel<<<1, 1024, 0, st>>>(last, reinterpret_cast<double *>(S->peer_box[1] + box_row_off(0, wb, ny)), ny,
-                                                     reinterpret_cast<volatile unsigned *>(S->peer_box[1] + box_flag_off(0, ny)), cur);
-            h->launches += 1;
-        }
-    }
-    // the halo rows of the final state (the rows pushed at the last tick)
+    double *box_top = reinterpret_cast<double *>(S->d_box + box_row_off(0, 0, ny));
+    double *box_bot = reinterpret_cast<double *>(S->d_box + box_row_off(1, 0, ny));
+    volatile unsigned *flag_up = up ? reinterpret_cast<volatile unsigned *>(S->peer_box[0] + box_flag_off(1, ny)) : nullptr;
+    volatile unsigned *flag_dn = dn ? reinterpret_cast<volatile unsigned *>(S->peer_box[1] + box_flag_off(0, ny)) : nullptr;
+    static const bool nowait = getenv("NNS_SLAB_ABL_NOWAIT") != nullptr;     // timing ablation only: results are wrong
+    auto wait_flags = [&](unsigned v) -> int {
+        if (nowait) return NNS_OK;
+        if (up && S->StreamWaitValue32((CUstream)st, (CUdeviceptr)(S->d_box + box_flag_off(0, ny)), v, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) { set_error("cuStreamWaitValue32 failed"); return NNS_ERR_CUDA; }
+        if (dn && S->StreamWaitValue32((CUstream)st, (CUdeviceptr)(S->d_box + box_flag_off(1, ny)), v, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) { set_error("cuStreamWaitValue32 failed"); return NNS_ERR_CUDA; }
+        return NNS_OK;
+    };
+    // start images: the whole boundary rows once.  The neighbours may still be reading their mailboxes for the
+    // previous run of sweeps only if they have not finished it -- they have: every rank raises its last flag after
+    // its last tick, and the waits below were passed.
     {
-        const unsigned prev = S->seq;
-        const int rb = prev & 1;
-        if (up) {
-            if (S->StreamWaitValue32((CUstream)st, (CUdeviceptr)(S->d_box + box_flag_off(0, ny)), prev, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) { set_error("cuStreamWaitValue32 failed"); return NNS_ERR_CUDA; }
-            NNS_CUDA(cudaMemcpyAsync(top_halo, S->d_box + box_row_off(0, rb, ny), sizeof(double) * ny, cudaMemcpyDeviceToDevice, st));
-        }
-        if (dn) {
-            if (S->StreamWaitValue32((CUstream)st, (CUdeviceptr)(S->d_box + box_flag_off(1, ny)), prev, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) { set_error("cuStreamWaitValue32 failed"); return NNS_ERR_CUDA; }
-            NNS_CUDA(cudaMemcpyAsync(bot_halo, S->d_box + box_row_off(1, rb, ny), sizeof(double) * ny, cudaMemcpyDeviceToDevice, st));
-        }
+        const unsigned cur = ++S->seq;
+        if (up) { slab_push_row_kernel<<<1, 1024, 0, st>>>(first, reinterpret_cast<double *>(S->peer_box[0] + box_row_off(1, 0, ny)), ny, flag_up, cur); h->launches += 1; }
+        if (dn) { slab_push_row_kernel<<<1, 1024, 0, st>>>(last, reinterpret_cast<double *>(S->peer_box[1] + box_row_off(0, 0, ny)), ny, flag_dn, cur); h->launches += 1; }
+    }
+    a.halo_top = up ? box_top : nullptr;
+    a.halo_bot = dn ? box_bot : nullptr;
+    a.push_up = up ? reinterpret_cast<double *>(S->peer_box[0] + box_row_off(1, 0, ny)) : nullptr;
+    a.push_dn = dn ? reinterpret_cast<double *>(S->peer_box[1] + box_row_off(0, 0, ny)) : nullptr;
+    a.first_row = S->row0; a.last_row = S->row0 + S->nrows - 1;
+    for (int T = 0; T <= Tmax; ++T) {
+        if ((rc = wait_flags(S->seq))) return rc;          // the neighbours' rows of the previous tick (or the start images)
+        if ((rc = launch_sweep(h, S, a, S->I0, S->I1, T, st))) return rc;
+        const unsigned cur = ++S->seq;
+        slab_flag_kernel<<<1, 1, 0, st>>>(flag_up, flag_dn, cur);
+        h->launches += 1;
+    }
+    // the halo rows of the final state, for the kernels that follow
+    if ((rc = wait_flags(S->seq))) return rc;
+    if (up) NNS_CUDA(cudaMemcpyAsync(top_halo, box_top, sizeof(double) * ny, cudaMemcpyDeviceToDevice, st));
+    if (dn) NNS_CUDA(cudaMemcpyAsync(bot_halo, box_bot, sizeof(double) * ny, cudaMemcpyDeviceToDevice, st));
+    // nobody may overwrite this rank's mailbox (the start images of the next run) before these copies are done:
+    // the neighbours wait for this rank's next flag, which is raised after them in stream order
+    {
+        const unsigned cur = ++S->seq;
+        slab_flag_kernel<<<1, 1, 0, st>>>(flag_up, flag_dn, cur);
+        h->launches += 1;
     }
     NNS_CUDA(cudaGetLastError());
     return NNS_OK;
