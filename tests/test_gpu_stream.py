@@ -192,3 +192,41 @@ def test_wave_kernel_early_exit_members_take_the_rerun_pass(oracle_fd, monkeypat
         assert rel_l2(v[b].cpu().numpy(), ov[-1]) <= TOL
         assert rel_l2(p[b].cpu().numpy(), op[-1]) <= TOL
     assert min(seen) < 49 and max(seen) == 49, seen
+
+
+def test_full_size_ensemble_4096_members(oracle_fd, monkeypatch):
+    """BASELINE config 4 at full size (4096 members, the bench workload), two steps: sampled members against the
+    oracle (fp64 rel-L2 <= 1e-10, sweep counts exact) and, as the size-independent property, every sampled
+    member bit-identical to the same member stepped in a batch of its own (members never interact, whichever
+    persistent CTA and position in its queue they land on)."""
+    import torch
+    monkeypatch.delenv("NNS_CHIP_MODE", raising=False)
+    monkeypatch.delenv("NNS_STREAM_MODE", raising=False)
+    from nns_b200.ensemble import cavity_bcs, cavity_ensemble_params
+    B = 4096
+    lid, nu = cavity_ensemble_params(B, seed=0)
+    dx = dy = 2. / (NX - 1)
+    u_bc, v_bc, p_bc = cavity_bcs(dx, dy)
+    ens = _ens(B, u_bc, v_bc, p_bc, nu, lid)
+    ens.init_variables()
+    sw = []
+    for _ in range(2):
+        ens.step()
+        sw.append(ens.sweeps.clone())
+    assert bool(torch.isfinite(ens.p).all())
+    sample = [0, 147, 148, 2047, 4000, 4095]
+    small = _ens(len(sample), u_bc, v_bc, p_bc, nu[sample], lid[sample])
+    small.init_variables()
+    for _ in range(2):
+        small.step()
+    z = np.zeros((NX, NY))
+    for k, b in enumerate(sample):
+        assert torch.equal(ens.u[b], small.u[k]) and torch.equal(ens.v[b], small.v[k]) and torch.equal(ens.p[b], small.p[k])
+        ub = _bc_tuples(u_bc)
+        ub[1] = ("right", "dirichlet", float(lid[b]))
+        ou, ov, op, osw = oracle_fd.chorin_simulate(z, z, z, ub, _bc_tuples(v_bc), _bc_tuples(p_bc), nt=2, nit=50,
+                                                    dt=2e-4, rho=1, nu=float(nu[b]), beta=1.25)
+        assert rel_l2(ens.u[b].cpu().numpy(), ou[-1]) <= TOL
+        assert rel_l2(ens.v[b].cpu().numpy(), ov[-1]) <= TOL
+        assert rel_l2(ens.p[b].cpu().numpy(), op[-1]) <= TOL
+        assert [int(s[b]) for s in sw] == list(osw)
