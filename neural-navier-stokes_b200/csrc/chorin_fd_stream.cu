@@ -369,13 +369,16 @@ __device__ void stencil_pass1(const StreamArgs &a, Ring<C::NY, NGR> &ring, const
         aE = ring.row(g, 2, GR - 1)[je]; aW = ring.row(g, 2, GR - 1)[jw]; bE = ring.row(g, 3, GR - 1)[je]; bW = ring.row(g, 3, GR - 1)[jw];
         ring.release(g);
         if (g + NGR < NGROUPS) {
+            NNS_FINE(const long long ti0 = NNS_PROF_T();)
             if (ts == 0) ring.template issue<4>(g + NGR, src);
+            NNS_FINE(if (a.prof && ts == 0) a.prof[(size_t)blockIdx.x * NPROF + 6] += clock64() - ti0;)
             if (g + NGR + 2 < NGROUPS) ring.template prefetch_l2<4>(g + NGR + 2, src, ts);
         }
     }
     uN = uC; vN = vC; uC = uS; vC = vS;                    // last row (an edge: copied)
     do_row(NX - 1);
     ring.g0 += NGROUPS;
+    NNS_FINE(if (a.prof && ts == 32) a.prof[(size_t)blockIdx.x * NPROF + 7] += clock64() - tp0;)
     NNS_FINE(NNS_PROF_ADD(18, tp0); if (a.prof && lead) a.prof[(size_t)blockIdx.x * NPROF + 17] += twait; tp0 = NNS_PROF_T();)
     __threadfence_block();
     named_sync(BAR_ST, NT_ST);
@@ -1084,7 +1087,7 @@ void chorin_stream_prof_dump(nns_handle *h) {
     cudaMemcpy(v.data(), pl->d_prof, sizeof(long long) * v.size(), cudaMemcpyDeviceToHost);
     cudaMemset(pl->d_prof, 0, sizeof(long long) * v.size());
     static const char *nm[NPROF] = {"sor.load_p", "sor.wait_ready", "sor.pull_cimg", "sor.wavefront", "sor.reduce_redo",
-                                    "sor.store_p", "", "", "st.pass1", "st.wait_consumed/fill", "st.wait_done", "st.pass2",
+                                    "sor.store_p", "p1.producer_issue(w0)", "p1.row_loop(w1)", "st.pass1", "st.wait_consumed/fill", "st.wait_done", "st.pass2",
                                     "sor.sweep_cyc(t0)", "sor.sweeps(t0)", "sor.sweep_cyc(t128)", "sor.sweeps(t128)",
                                     "p1.prologue", "p1.wait_full", "p1.row_loop", "p1.bcs", "p1.patch", "p2.edges_bcs",
                                     "p2.wait_full", "p2.row_loop", "sor.sweep_cyc(w0)", "sor.sweep_cyc(w1)", "sor.sweep_cyc(w2)",
