@@ -18,6 +18,7 @@
 // Hand-offs inside the CTA use named barriers (bar.arrive / bar.sync) in a full/empty protocol; the
 // C' image of the next member and the intermediate velocities travel through L2-resident global memory.
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "nns_common.cuh"
@@ -903,89 +904,100 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_wave_kernel(const St
             }
         };
         unsigned long long mask = 0ull, amb = 0ull;
-        int kw = 0, tl = -amin;
         long long tsw = 0;
         const long long tk0 = NNS_PROF_T();
-        for (int T = 0; T <= tend; ++T, ++tl) {
-            if (tl == per) { tl = 0; ++kw; }
-            if (tl >= 0 && kw < nmine) {
-                const int m = blockIdx.x + kw * gridDim.x;
-                if (tl == 0) {
-                    if (kw == 0) fetch(m);
-                    cp_async_wait_all();
-                    const long long t0 = NNS_PROF_T();
-                    spin_until_ge(&s_cready[w], kw + 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    NNS_PROF_ADD(1, t0);
-                    __syncwarp();
-                }
+        // Every warp passes tend + 1 stage barriers: amin before its first member, per for every member (last + 1
+        // sweep stages -- an even number: top / bottom pairs --, one report stage, idle stages), the rest at the end.
+        // The member changes sit outside the hot loop, which only holds the two sweeps and their barriers.
+        auto sweep = [&](int kw, int tl, auto top) {
 #ifndef NNS_ABL_NOSWEEP      // timing ablation: the stencil role alone on the SM
-#ifdef NNS_WAVE_TRACE_BUILD
-                const bool tracing = a.trace && blockIdx.x == 0 && lane == 0 && kw == 1 && T - per >= 40 && T - per < 56;
-                if (tracing) a.trace[((size_t)w * 16 + (T - per - 40)) * 4 + 0] = clock64();
+            const long long t0 = NNS_PROF_T();
+            const int q = tl - delta;
+            const bool act = q >= 0 && q <= 2 * cap - 1;
+            const int sidx = q >> 1;
+            const uint32_t tmc = tm_mine + (uint32_t)(128 * (kw & 1));
+            unsigned mhi = 0u;
+            if (decltype(top)::value) block_sweep_tm<BR, BC, RS, 0, RS>(P, tmc, h, k, act, sidx != cap - 1, mhi);
+            else block_sweep_tm<BR, BC, RS, RS, BR>(P, tmc, h, k, act, sidx != cap - 1, mhi);
+            if (act) {
+                mask |= (unsigned long long)(mhi > tolhi) << sidx;
+                amb |= (unsigned long long)(mhi == tolhi) << sidx;
+            }
+            if (a.prof && lane == 0) tsw += clock64() - t0;
 #endif
-                if (tl <= last) {
-                    const long long t0 = NNS_PROF_T();
-                    const int q = tl - delta;
-                    const bool act = q >= 0 && q <= 2 * cap - 1;
-                    const int sidx = q >> 1;
-                    const uint32_t tmc = tm_mine + (uint32_t)(128 * (kw & 1));
-                    unsigned mhi = 0u;
-                    if (!(tl & 1)) block_sweep_tm<BR, BC, RS, 0, RS>(P, tmc, h, k, act, sidx != cap - 1, mhi);
-                    else block_sweep_tm<BR, BC, RS, RS, BR>(P, tmc, h, k, act, sidx != cap - 1, mhi);
-                    if (act) {
-                        mask |= (unsigned long long)(mhi > tolhi) << sidx;
-                        amb |= (unsigned long long)(mhi == tolhi) << sidx;
-                    }
-                    if (a.prof && lane == 0) tsw += clock64() - t0;
-                }
-#endif
-                if (tl == last) {
-                    // the warp has finished member kw: results to the scratch image, next member's loads in flight
-                    double *ps = pscr + (size_t)(kw & 1) * N;
+        };
+        using TopT = std::integral_constant<bool, true>;
+        using BotT = std::integral_constant<bool, false>;
+        int passed = 0;
+        for (; passed < amin; ++passed) named_sync(BAR_SOR, NT_SOR);
+        for (int kw = 0; kw < nmine; ++kw) {
+            const int m = blockIdx.x + kw * gridDim.x;
+            // ---- start of the member (local stage 0)
+            if (kw == 0) fetch(m);
+            cp_async_wait_all();
+            {
+                const long long t0 = NNS_PROF_T();
+                spin_until_ge(&s_cready[w], kw + 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                NNS_PROF_ADD(1, t0);
+                __syncwarp();
+            }
+            // ---- hot loop: local stages 0 .. last - 2 in top / bottom pairs
+#pragma unroll 1
+            for (int tl = 0; tl + 1 < last; tl += 2) {
+                sweep(kw, tl, TopT{});
+                named_sync(BAR_SOR, NT_SOR);
+                sweep(kw, tl + 1, BotT{});
+                named_sync(BAR_SOR, NT_SOR);
+            }
+            sweep(kw, last - 1, TopT{});
+            named_sync(BAR_SOR, NT_SOR);
+            sweep(kw, last, BotT{});
+            // ---- local stage `last`: the warp has finished member kw: results to the scratch image, next member's
+            // loads in flight
+            {
+                double *ps = pscr + (size_t)(kw & 1) * N;
 #ifdef NNS_ABL_NOTRANS       // timing ablation: no block stores / loads at the member changes
-                    if (false) {
+                if (false) {
 #else
-                    if (owner) {
+                if (owner) {
 #endif
 #pragma unroll
-                        for (int li = 0; li < BR; ++li)
+                    for (int li = 0; li < BR; ++li)
 #pragma unroll
-                            for (int lj = 0; lj < BC; ++lj) ps[(size_t)(r0 + li) * NY + c0 + lj] = P[li][lj];
-                    }
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) s_wdone[w] = kw + 1;
-#ifndef NNS_ABL_NOTRANS
-                    if (kw + 1 < nmine) fetch(m + gridDim.x);
-#endif
+                        for (int lj = 0; lj < BC; ++lj) ps[(size_t)(r0 + li) * NY + c0 + lj] = P[li][lj];
                 }
-                if (tl == last + 1) {
-                    const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)mask), hi = __reduce_or_sync(0xffffffffu, (unsigned)(mask >> 32));
-                    const unsigned alo = __reduce_or_sync(0xffffffffu, (unsigned)amb), ahi = __reduce_or_sync(0xffffffffu, (unsigned)(amb >> 32));
-                    mask = 0ull; amb = 0ull;
-                    // the p blocks of every lane before the warp reports: the readers are threads of this CTA (generic
-                    // proxy) and bulk copies issued by them (async proxy)
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) s_wdone[w] = kw + 1;
+#ifndef NNS_ABL_NOTRANS
+                if (kw + 1 < nmine) fetch(m + gridDim.x);
+#endif
+            }
+            named_sync(BAR_SOR, NT_SOR);
+            // ---- local stage last + 1: the warp reports
+            {
+                const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)mask), hi = __reduce_or_sync(0xffffffffu, (unsigned)(mask >> 32));
+                const unsigned alo = __reduce_or_sync(0xffffffffu, (unsigned)amb), ahi = __reduce_or_sync(0xffffffffu, (unsigned)(amb >> 32));
+                mask = 0ull; amb = 0ull;
+                // the p blocks of every lane before the warp reports: the readers are threads of this CTA (generic
+                // proxy) and bulk copies issued by them (async proxy)
+                __threadfence_block();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    atomicOr(&s_mask[kw & 1][0], ((unsigned long long)hi << 32) | lo);
+                    atomicOr(&s_mask[kw & 1][1], ((unsigned long long)ahi << 32) | alo);
                     __threadfence_block();
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) {
-                        atomicOr(&s_mask[kw & 1][0], ((unsigned long long)hi << 32) | lo);
-                        atomicOr(&s_mask[kw & 1][1], ((unsigned long long)ahi << 32) | alo);
-                        __threadfence_block();
-                        s_wstored[w] = kw + 1;
-                    }
+                    s_wstored[w] = kw + 1;
                 }
             }
-#ifdef NNS_WAVE_TRACE_BUILD
-            const bool tracing2 = a.trace && blockIdx.x == 0 && lane == 0 && kw == 1 && T - per >= 40 && T - per < 56;
-            if (tracing2) a.trace[((size_t)w * 16 + (T - per - 40)) * 4 + 1] = clock64();
             named_sync(BAR_SOR, NT_SOR);
-            if (tracing2) a.trace[((size_t)w * 16 + (T - per - 40)) * 4 + 2] = clock64();
-#else
-            named_sync(BAR_SOR, NT_SOR);
-#endif
+            // ---- idle stages up to the end of the member's period
+            for (int tl = last + 2; tl < per; ++tl) named_sync(BAR_SOR, NT_SOR);
+            passed += per;
         }
+        for (; passed <= tend; ++passed) named_sync(BAR_SOR, NT_SOR);
         if (a.prof && lead) {
             a.prof[(size_t)blockIdx.x * NPROF + 3] += clock64() - tk0;
             a.prof[(size_t)blockIdx.x * NPROF + 12] += tsw;
