@@ -146,6 +146,10 @@ __device__ __forceinline__ void wavefront(double (&P)[BR][BC], const double2 *Cm
     if (owner) publish<BR, BC, 0, BR>(P, h);   // the whole perimeter once
     named_sync(BAR_SOR, NT_SOR);
     const unsigned tolhi = (unsigned)(tolbits >> 32);
+    // (Splitting this loop into top / bottom stage pairs with the sub-block kind fixed at compile time, as the wave
+    // kernel does, is 2 % faster here too -- 4.42 ms/step -- but made the results of this kernel NON-DETERMINISTIC
+    // (about 1 % of the members of later rounds off by 1e-6 .. 1e-2 from run to run, scripts/determinism_check.py); the
+    // cause was not found, so the single loop stays.)
     for (int T = 0; T <= tmax; ++T) {
         const int q = T - sd;                       // 2s for the top sub-block, 2s + 1 for the bottom one
         const bool work = owner && q >= 0 && q <= 2 * (cap - 1) + 1;
