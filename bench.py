@@ -127,7 +127,7 @@ def cpu_port_throughput(nx, ny, nit, dt, budget_s, steps_per_call=1, members=Non
     a short calibration run so that it takes about `budget_s` seconds on this host."""
     from oracle import fd as ofd
     ofd.build()
-    T = ofd.max_threads()
+    T = ofd.set_threads()           # every host core, whatever OMP_NUM_THREADS says (torchrun exports 1)
 
     def once(m):
         u, v, p, nu, u_bcs, v_bc, p_bc = cavity_oracle_sample(nx, ny, m, nit, dt)
@@ -145,6 +145,15 @@ def cpu_port_throughput(nx, ny, nit, dt, budget_s, steps_per_call=1, members=Non
     return members * nx * ny * steps_per_call / el, used, members, el, state
 
 
+def workload_config(workload, nx, ny, B, world, nit, dt):
+    """The `config` object of the JSON line: identical for the b200 and the reference arm."""
+    return {"workload": workload, "nx": nx, "ny": ny, "members_per_gpu": B, "global_members": B * world,
+            "nit": nit, "dt": dt, "beta": 1.25, "method": "explicit",
+            "parallelism": "ensemble members sharded, no collective",
+            "l2": "state per GPU %.2f GB >> 126 MB L2 (inputs larger than L2, no flush needed)"
+                  % (5 * B * nx * ny * 8 / 1e9)}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference algorithm on the host cores.  The reference itself is
     pure Python (2.7 us per cell-sweep) and is not on this box; its C restatement (oracle port,
@@ -152,9 +161,11 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     nx, ny, B, nit, dt = WORKLOADS[args.workload]
+    if args.members:
+        B = args.members
     from oracle import fd as ofd
     ofd.build()
-    T = ofd.max_threads()
+    T = ofd.set_threads()           # every host core, whatever OMP_NUM_THREADS says (torchrun exports 1)
     members = int(min(B, max(T, 8 * T)))
     _, _, _, _, st = cpu_port_throughput(nx, ny, nit, dt, 0, 1, members)      # allocs + first touch
     u, v, u1, v1, p, nu, u_bcs, v_bc, p_bc = st
@@ -170,7 +181,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "nx": nx, "ny": ny, "members_per_gpu": B, "nit": nit, "dt": dt},
+        "config": workload_config(args.workload, nx, ny, B, world, nit, dt),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": T, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -251,7 +262,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ensemble4096_cavity128", choices=sorted(WORKLOADS) + sorted(SLAB_WORKLOADS))
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--members", type=int, default=None, help="override members per GPU")
     args = ap.parse_args()
@@ -366,13 +377,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "nx": nx, "ny": ny, "members_per_gpu": B,
-                       "global_members": B * world, "nit": nit, "dt": dt, "beta": 1.25, "method": "explicit",
-                       "parallelism": "ensemble members sharded, no collective",
-                       "l2": "state per GPU %.2f GB >> 126 MB L2 (inputs larger than L2, no flush needed)"
-                             % (5 * B * nx * ny * 8 / 1e9),
-                       "sweeps_per_step_last": [int(sweeps_last.min()), int(sweeps_last.max())],
-                       "finite": finite},
+            "config": workload_config(args.workload, nx, ny, B, world, nit, dt),
+            "checks": {"sweeps_per_step_last": [int(sweeps_last.min()), int(sweeps_last.max())], "finite": finite},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

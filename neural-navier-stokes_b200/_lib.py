@@ -125,6 +125,15 @@ class Handle:
                                 FLAG_CHECK_FINITE if check_finite else 0)
         arr, n = bc_table(u_bc, v_bc, p_bc)
         self.n_bcs = n
+        # the kernels apply Neumann conditions with the solver's spacing; the reference uses the BC object's own
+        # dx / dy (src/boundary.py:75-84): a non-zero flux built with another spacing would silently differ
+        sdx, sdy = (2. / nx, 2. / ny) if solver == SOLVER_CHORIN_SPECTRAL else (2. / (nx - 1), 2. / (ny - 1))
+        for bc in list(u_bc or ()) + list(v_bc or ()) + list(p_bc or ()):
+            if getattr(bc, "type", None) == "neumann" and float(bc.value) != 0.0:
+                d, s = (bc.dx, sdx) if bc.boundary in ("left", "right") else (bc.dy, sdy)
+                if abs(float(d) - s) > 1e-14 * abs(s):
+                    raise ValueError("Neumann boundary condition on %r was built with spacing %r, the solver uses %r"
+                                     % (bc.boundary, d, s))
         nu_ptr = bv_ptr = None
         if nu_per_member is not None:
             self._nu = np.ascontiguousarray(nu_per_member, dtype=np.float64)

@@ -39,8 +39,17 @@ class NavierStokesSystem():
         self.last_sweeps = None      # int32 (nsteps,) SOR sweeps executed per step of the last call
 
     # -- device handle (created on first use; raises without the CUDA library / a GPU) -----
+    def _key(self):
+        bcs = tuple((bc.type, bc.boundary, float(bc.value)) for lst in (self.u_bc, self.v_bc, self.p_bc) for bc in lst)
+        return (self.nx, self.ny, self.nit, self.dt, self.rho, self.nu, self.beta, self.method, bcs)
+
     def _h(self):
+        # the reference reads its attributes at every step: rebuild the device handle when they have changed
+        if self._handle is not None and self._handle_key != self._key():
+            self._handle.close()
+            self._handle = None
         if self._handle is None:
+            self._handle_key = self._key()
             if self.method not in _lib.METHODS:
                 raise Exception('method not recognized: {}'.format(self.method))
             self._handle = _lib.Handle(_lib.SOLVER_CHORIN_FD, self.nx, self.ny, self.nit, self.dt, self.rho,

@@ -45,7 +45,12 @@ class NavierStokesSystem():
         self.DxDPx_lambda, self.DxDPx_P_inv = o.pres['lx'], o.pres['Pinv']
 
     def _h(self):
+        # dt and rho are read at every step by the reference (the operators are fixed at construction, :41-52)
+        if self._handle is not None and self._handle_key != (self.dt, self.rho):
+            self._handle.close()
+            self._handle = None
         if self._handle is None:
+            self._handle_key = (self.dt, self.rho)
             if not self.ops.is_real():
                 raise ComplexWarning("Casting complex values to real discards the imaginary part")
             h = _lib.Handle(_lib.SOLVER_CHORIN_SPECTRAL, self.nx, self.ny, self.nit, self.dt, self.rho, self.nu,

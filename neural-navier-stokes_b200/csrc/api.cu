@@ -63,6 +63,26 @@ int spectral_correct(nns_handle *h, const double *ui, const double *vi, const do
 int spectral_run(nns_handle *h, double *bufU[3], double *bufV[3], double *p, int nsteps, double *tu, double *tv,
                  double *tp, cudaStream_t st);
 
+// Cached device buffers of the host-buffer entry points: allocated once per handle and grown on demand, so that a
+// user loop over step() / simulate() does not pay cudaMalloc / cudaFree (and their device synchronisation) per call.
+static int pool_get(nns_handle *h, int k, size_t bytes, void **out) {
+    if (h->pool_bytes[k] < bytes) {
+        cudaFree(h->d_pool[k]);
+        h->d_pool[k] = nullptr;
+        h->pool_bytes[k] = 0;
+        NNS_CUDA(cudaMalloc(&h->d_pool[k], bytes));
+        h->pool_bytes[k] = bytes;
+    }
+    *out = h->d_pool[k];
+    return NNS_OK;
+}
+
+// The reference raises per call (warnings are errors): the counter of non-finite values restarts with every host call.
+static int reset_nonfinite(nns_handle *h, cudaStream_t st) {
+    NNS_CUDA(cudaMemsetAsync(h->d_nonfinite, 0, sizeof(unsigned long long), st));
+    return NNS_OK;
+}
+
 static int ensure_scratch(nns_handle *h, int k) {
     if (h->d_scratch[k]) return NNS_OK;
     NNS_CUDA(cudaMalloc(&h->d_scratch[k], sizeof(double) * (size_t)h->g.nx * h->g.ny * h->g.batch));
@@ -126,8 +146,19 @@ extern "C" {
 int32_t nns_abi_version(void) { return NNS_ABI_VERSION; }
 const char *nns_last_error(void) { return g_err; }
 
+static int32_t create_impl(const nns_params *P, const nns_bc *bcs, int32_t n_bcs, const double *nu_b,
+                           const double *bcval_b, nns_handle **out, nns_handle **partial);
+
 int32_t nns_create(const nns_params *P, const nns_bc *bcs, int32_t n_bcs, const double *nu_b,
                    const double *bcval_b, nns_handle **out) {
+    nns_handle *partial = nullptr;
+    const int32_t rc = create_impl(P, bcs, n_bcs, nu_b, bcval_b, out, &partial);
+    if (rc != NNS_OK && partial) nns_destroy(partial);      // no leak of the handle / its device buffers on a failed create
+    return rc;
+}
+
+static int32_t create_impl(const nns_params *P, const nns_bc *bcs, int32_t n_bcs, const double *nu_b,
+                           const double *bcval_b, nns_handle **out, nns_handle **partial) {
     if (!P || !out || (n_bcs > 0 && !bcs)) { set_error("nns_create: null argument"); return NNS_ERR_INVALID; }
     *out = nullptr;
     if (P->nx < 3 || P->ny < 3 || P->batch < 1 || P->nit < 0) {
@@ -155,6 +186,7 @@ int32_t nns_create(const nns_params *P, const nns_bc *bcs, int32_t n_bcs, const 
     nns_handle *h = new (std::nothrow) nns_handle();
     if (!h) { set_error("out of host memory"); return NNS_ERR_NOMEM; }
     memset(h, 0, sizeof(*h));
+    *partial = h;
     h->params = *P;
     if (P->device >= 0) h->device = P->device;
     else NNS_CUDA(cudaGetDevice(&h->device));
@@ -172,11 +204,10 @@ int32_t nns_create(const nns_params *P, const nns_bc *bcs, int32_t n_bcs, const 
         const nns_bc &b = bcs[k];
         if (b.field < 0 || b.field > 2 || b.side < 0 || b.side > 3 || b.type < 0 || b.type > 1) {
             set_error("nns_create: bad boundary condition #%d (field %d side %d type %d)", k, b.field, b.side, b.type);
-            delete h;
             return NNS_ERR_INVALID;
         }
         BcList &L = h->bc[b.field];
-        if (L.n >= NNS_MAX_BC) { set_error("more than %d boundary conditions on one field", NNS_MAX_BC); delete h; return NNS_ERR_INVALID; }
+        if (L.n >= NNS_MAX_BC) { set_error("more than %d boundary conditions on one field", NNS_MAX_BC); return NNS_ERR_INVALID; }
         L.side[L.n] = b.side; L.type[L.n] = b.type; L.value[L.n] = b.value; L.slot[L.n] = k;
         L.n++;
     }
@@ -192,6 +223,7 @@ int32_t nns_create(const nns_params *P, const nns_bc *bcs, int32_t n_bcs, const 
     NNS_CUDA(cudaMemset(h->d_nonfinite, 0, sizeof(unsigned long long)));
     NNS_CUDA(cudaMalloc(&h->d_sweeps, sizeof(int32_t) * g.batch));
     *out = h;
+    *partial = nullptr;
     return NNS_OK;
 }
 
@@ -207,6 +239,7 @@ int32_t nns_destroy(nns_handle *h) {
     spectral_destroy(h);
     for (int k = 0; k < 4; ++k) cudaFree(h->d_scratch[k]);
     for (int k = 0; k < 7; ++k) cudaFree(h->d_stage[k]);
+    for (int k = 0; k < 10; ++k) cudaFree(h->d_pool[k]);
     for (int k = 0; k < 4; ++k) if (h->streams[k]) cudaStreamDestroy(h->streams[k]);
     delete h;
     return NNS_OK;
@@ -286,12 +319,6 @@ int32_t nns_chorin_fd_correct(nns_handle *h, const double *ui, const double *vi,
 
 // Host-buffer helpers ------------------------------------------------------------------------
 namespace {
-struct DevBuf {
-    double *p = nullptr;
-    ~DevBuf() { cudaFree(p); }
-    int alloc(size_t bytes) { NNS_CUDA(cudaMalloc(&p, bytes)); return NNS_OK; }
-};
-
 // Large device -> pageable-host copies (the trajectories of the *_run_host entry points: the reference's simulate()
 // returns (nt, nx, ny) numpy arrays) through two pinned staging buffers: the DMA of chunk i + 1 overlaps the host
 // memcpy of chunk i.  A plain cudaMemcpy into pageable memory ran at ~2 GB/s (3.1 GB of direct_fd 256^2
@@ -326,39 +353,39 @@ int d2h_staged(void *dst, const void *src, size_t bytes) {
 }
 }  // namespace
 
-int32_t nns_chorin_fd_run_host(nns_handle *h, double *u, double *v, double *u1, double *v1, double *p,
-                               int32_t nsteps, double *tu, double *tv, double *tp, int32_t *sweeps_out) {
-    NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_FD);
-    if (!u || !v || !u1 || !v1 || !p || nsteps < 0) { set_error("nns_chorin_fd_run_host: bad argument"); return NNS_ERR_INVALID; }
+}  // extern "C" (templates need C++ linkage)
+
+// Shared body of the *_run_host entry points: fields (and optional trajectories / sweep counts) through cached device
+// buffers; `run` advances the device state.
+template <typename Run>
+static int32_t run_host_common(nns_handle *h, int nfields, double *const *hostf, int32_t nsteps, double *const *hostt,
+                               int32_t *sweeps_out, const char *what, Run &&run) {
     const size_t bytes = sizeof(double) * (size_t)h->g.nx * h->g.ny * h->g.batch;
-    DevBuf f[5], t[3];
-    int32_t *dsw = nullptr;
     int rc;
-    double *hostf[5] = {u, v, u1, v1, p};
-    for (int k = 0; k < 5; ++k) {
-        if ((rc = f[k].alloc(bytes))) return rc;
-        NNS_CUDA(cudaMemcpy(f[k].p, hostf[k], bytes, cudaMemcpyHostToDevice));
+    double *f[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *t[3] = {nullptr, nullptr, nullptr};
+    int32_t *dsw = nullptr;
+    if ((rc = reset_nonfinite(h, nullptr))) return rc;
+    for (int k = 0; k < nfields; ++k) {
+        if ((rc = pool_get(h, k, bytes, reinterpret_cast<void **>(&f[k])))) return rc;
+        NNS_CUDA(cudaMemcpyAsync(f[k], hostf[k], bytes, cudaMemcpyHostToDevice, nullptr));
     }
-    double *hostt[3] = {tu, tv, tp};
-    const bool traj = tu && tv && tp && nsteps > 0;
+    const bool traj = hostt[0] && hostt[1] && hostt[2] && nsteps > 0;
     if (traj)
         for (int k = 0; k < 3; ++k)
-            if ((rc = t[k].alloc(bytes * nsteps))) return rc;
-    if (sweeps_out && nsteps > 0) NNS_CUDA(cudaMalloc(&dsw, sizeof(int32_t) * (size_t)nsteps * h->g.batch));
-    rc = nns_chorin_fd_run(h, f[0].p, f[1].p, f[2].p, f[3].p, f[4].p, nsteps, traj ? t[0].p : nullptr,
-                           traj ? t[1].p : nullptr, traj ? t[2].p : nullptr, dsw, nullptr);
+            if ((rc = pool_get(h, 5 + k, bytes * nsteps, reinterpret_cast<void **>(&t[k])))) return rc;
+    if (sweeps_out && nsteps > 0 && (rc = pool_get(h, 8, sizeof(int32_t) * (size_t)nsteps * h->g.batch, reinterpret_cast<void **>(&dsw)))) return rc;
+    rc = run(f, t, dsw);
     if (rc == NNS_OK) {
-        cudaError_t e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) { set_error("kernel failed: %s", cudaGetErrorString(e)); rc = NNS_ERR_CUDA; }
+        for (int k = 0; k < nfields; ++k) cudaMemcpyAsync(hostf[k], f[k], bytes, cudaMemcpyDeviceToHost, nullptr);
+        cudaError_t e = cudaStreamSynchronize(nullptr);
+        if (e != cudaSuccess) { set_error("%s: kernel failed: %s", what, cudaGetErrorString(e)); rc = NNS_ERR_CUDA; }
     }
     if (rc == NNS_OK) {
-        for (int k = 0; k < 5; ++k) cudaMemcpy(hostf[k], f[k].p, bytes, cudaMemcpyDeviceToHost);
-        if (traj) for (int k = 0; k < 3 && rc == NNS_OK; ++k) rc = d2h_staged(hostt[k], t[k].p, bytes * nsteps);
+        if (traj) for (int k = 0; k < 3 && rc == NNS_OK; ++k) rc = d2h_staged(hostt[k], t[k], bytes * nsteps);
         if (dsw) cudaMemcpy(sweeps_out, dsw, sizeof(int32_t) * (size_t)nsteps * h->g.batch, cudaMemcpyDeviceToHost);
         cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { set_error("copy back failed: %s", cudaGetErrorString(e)); rc = NNS_ERR_CUDA; }
+        if (e != cudaSuccess) { set_error("%s: copy back failed: %s", what, cudaGetErrorString(e)); rc = NNS_ERR_CUDA; }
     }
-    cudaFree(dsw);
     if (rc == NNS_OK && (h->params.flags & NNS_FLAG_CHECK_FINITE)) {
         int64_t c = 0;
         if (nns_nonfinite_count(h, &c) == NNS_OK && c > 0) {
@@ -367,6 +394,18 @@ int32_t nns_chorin_fd_run_host(nns_handle *h, double *u, double *v, double *u1, 
         }
     }
     return rc;
+}
+
+extern "C" {
+
+int32_t nns_chorin_fd_run_host(nns_handle *h, double *u, double *v, double *u1, double *v1, double *p,
+                               int32_t nsteps, double *tu, double *tv, double *tp, int32_t *sweeps_out) {
+    NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_FD);
+    if (!u || !v || !u1 || !v1 || !p || nsteps < 0) { set_error("nns_chorin_fd_run_host: bad argument"); return NNS_ERR_INVALID; }
+    double *hostf[5] = {u, v, u1, v1, p}, *hostt[3] = {tu, tv, tp};
+    return run_host_common(h, 5, hostf, nsteps, hostt, sweeps_out, "nns_chorin_fd_run_host", [&](double **f, double **t, int32_t *dsw) {
+        return nns_chorin_fd_run(h, f[0], f[1], f[2], f[3], f[4], nsteps, t[0], t[1], t[2], dsw, nullptr);
+    });
 }
 
 // One step with HOST buffers, mirroring the reference's step(un, vn, un1, vn1, p) -> (u, v, p):
@@ -389,11 +428,13 @@ int32_t nns_chorin_fd_step_host(nns_handle *h, const double *u, const double *v,
     const int dout[3] = {5, 6, 4};
     const int nchunks = B >= 1184 ? 8 : B >= 296 ? 2 : 1;     // keep >= 148 CTAs per launch
     const size_t per = (B + nchunks - 1) / nchunks;
-    int rc = NNS_OK;
+    int rc = reset_nonfinite(h, nullptr);
+    if (rc == NNS_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) { set_error("step_host: stream error"); rc = NNS_ERR_CUDA; }
     for (int c = 0; c < nchunks && rc == NNS_OK; ++c) {
         const size_t m0 = c * per, cnt = m0 + per <= B ? per : B - m0;
         if (m0 >= B) break;
         cudaStream_t st = h->streams[c % 4];
+        h->scratch_slot = c % 4;             // launches of different internal streams may overlap: one scratch set each
         const size_t off = m0 * N, cb = sizeof(double) * cnt * N;
         for (int k = 0; k < 5; ++k) NNS_CUDA(cudaMemcpyAsync(d[k] + off, hin[k] + off, cb, cudaMemcpyHostToDevice, st));
         double *bu[3] = {d[0] + off, d[2] + off, d[5] + off};
@@ -404,6 +445,7 @@ int32_t nns_chorin_fd_step_host(nns_handle *h, const double *u, const double *v,
         for (int k = 0; k < 3; ++k) NNS_CUDA(cudaMemcpyAsync(hout[k] + off, d[dout[k]] + off, cb, cudaMemcpyDeviceToHost, st));
         if (sweeps_out) NNS_CUDA(cudaMemcpyAsync(sweeps_out + m0, h->d_sweeps + m0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, st));
     }
+    h->scratch_slot = 0;
     for (int k = 0; k < 4; ++k) {
         cudaError_t e = cudaStreamSynchronize(h->streams[k]);
         if (e != cudaSuccess && rc == NNS_OK) { set_error("step_host: %s", cudaGetErrorString(e)); rc = NNS_ERR_CUDA; }
@@ -430,39 +472,10 @@ int32_t nns_direct_fd_run_host(nns_handle *h, double *u, double *v, double *p, i
                                double *tv, double *tp) {
     NNS_CHECK_HANDLE(h, NNS_SOLVER_DIRECT_FD);
     if (!u || !v || !p || nsteps < 0) { set_error("nns_direct_fd_run_host: bad argument"); return NNS_ERR_INVALID; }
-    const size_t bytes = sizeof(double) * (size_t)h->g.nx * h->g.ny * h->g.batch;
-    DevBuf f[3], t[3];
-    int rc;
-    double *hostf[3] = {u, v, p};
-    for (int k = 0; k < 3; ++k) {
-        if ((rc = f[k].alloc(bytes))) return rc;
-        NNS_CUDA(cudaMemcpy(f[k].p, hostf[k], bytes, cudaMemcpyHostToDevice));
-    }
-    double *hostt[3] = {tu, tv, tp};
-    const bool traj = tu && tv && tp && nsteps > 0;
-    if (traj)
-        for (int k = 0; k < 3; ++k)
-            if ((rc = t[k].alloc(bytes * nsteps))) return rc;
-    rc = nns_direct_fd_run(h, f[0].p, f[1].p, f[2].p, nsteps, traj ? t[0].p : nullptr, traj ? t[1].p : nullptr,
-                           traj ? t[2].p : nullptr, nullptr);
-    if (rc == NNS_OK) {
-        cudaError_t e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) { set_error("kernel failed: %s", cudaGetErrorString(e)); rc = NNS_ERR_CUDA; }
-    }
-    if (rc == NNS_OK) {
-        for (int k = 0; k < 3; ++k) cudaMemcpy(hostf[k], f[k].p, bytes, cudaMemcpyDeviceToHost);
-        if (traj) for (int k = 0; k < 3 && rc == NNS_OK; ++k) rc = d2h_staged(hostt[k], t[k].p, bytes * nsteps);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { set_error("copy back failed: %s", cudaGetErrorString(e)); rc = NNS_ERR_CUDA; }
-    }
-    if (rc == NNS_OK && (h->params.flags & NNS_FLAG_CHECK_FINITE)) {
-        int64_t c = 0;
-        if (nns_nonfinite_count(h, &c) == NNS_OK && c > 0) {
-            set_error("non-finite values in u/v/p (%lld cells)", (long long)c);
-            rc = NNS_ERR_NONFINITE;
-        }
-    }
-    return rc;
+    double *hostf[3] = {u, v, p}, *hostt[3] = {tu, tv, tp};
+    return run_host_common(h, 3, hostf, nsteps, hostt, nullptr, "nns_direct_fd_run_host", [&](double **f, double **t, int32_t *) {
+        return nns_direct_fd_run(h, f[0], f[1], f[2], nsteps, t[0], t[1], t[2], nullptr);
+    });
 }
 
 // ---- chorin_spectral --------------------------------------------------------------------------
@@ -511,39 +524,10 @@ int32_t nns_spectral_run_host(nns_handle *h, double *u, double *v, double *u1, d
                               int32_t nsteps, double *tu, double *tv, double *tp) {
     NNS_CHECK_SPECTRAL(h);
     if (!u || !v || !u1 || !v1 || !p || nsteps < 0) { set_error("nns_spectral_run_host: bad argument"); return NNS_ERR_INVALID; }
-    const size_t bytes = sizeof(double) * (size_t)h->g.nx * h->g.ny * h->g.batch;
-    DevBuf f[5], t[3];
-    int rc;
-    double *hostf[5] = {u, v, u1, v1, p};
-    for (int k = 0; k < 5; ++k) {
-        if ((rc = f[k].alloc(bytes))) return rc;
-        NNS_CUDA(cudaMemcpy(f[k].p, hostf[k], bytes, cudaMemcpyHostToDevice));
-    }
-    double *hostt[3] = {tu, tv, tp};
-    const bool traj = tu && tv && tp && nsteps > 0;
-    if (traj)
-        for (int k = 0; k < 3; ++k)
-            if ((rc = t[k].alloc(bytes * nsteps))) return rc;
-    rc = nns_spectral_run(h, f[0].p, f[1].p, f[2].p, f[3].p, f[4].p, nsteps, traj ? t[0].p : nullptr,
-                          traj ? t[1].p : nullptr, traj ? t[2].p : nullptr, nullptr);
-    if (rc == NNS_OK) {
-        cudaError_t e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) { set_error("kernel failed: %s", cudaGetErrorString(e)); rc = NNS_ERR_CUDA; }
-    }
-    if (rc == NNS_OK) {
-        for (int k = 0; k < 5; ++k) cudaMemcpy(hostf[k], f[k].p, bytes, cudaMemcpyDeviceToHost);
-        if (traj) for (int k = 0; k < 3 && rc == NNS_OK; ++k) rc = d2h_staged(hostt[k], t[k].p, bytes * nsteps);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { set_error("copy back failed: %s", cudaGetErrorString(e)); rc = NNS_ERR_CUDA; }
-    }
-    if (rc == NNS_OK && (h->params.flags & NNS_FLAG_CHECK_FINITE)) {
-        int64_t c = 0;
-        if (nns_nonfinite_count(h, &c) == NNS_OK && c > 0) {
-            set_error("non-finite values in u/v/p (%lld cells): the reference raises here (warnings are errors, chorin_spectral:3)", (long long)c);
-            rc = NNS_ERR_NONFINITE;
-        }
-    }
-    return rc;
+    double *hostf[5] = {u, v, u1, v1, p}, *hostt[3] = {tu, tv, tp};
+    return run_host_common(h, 5, hostf, nsteps, hostt, nullptr, "nns_spectral_run_host", [&](double **f, double **t, int32_t *) {
+        return nns_spectral_run(h, f[0], f[1], f[2], f[3], f[4], nsteps, t[0], t[1], t[2], nullptr);
+    });
 }
 
 // ---- chorin_fd on row slabs (one grid over several GPUs) ---------------------------------------

@@ -37,6 +37,7 @@ constexpr int RING = GR * NG;   // rows per field in the stencil ring
 constexpr int REGS_SOR = 200, REGS_ST = 104;
 constexpr int REGS_SOR_W = 200, REGS_ST_W = 104;     // setmaxnreg only moves registers inside the CTA's launch allocation (384 x 168)
 constexpr int NW_SOR = NT_SOR / 32;
+constexpr int N_SCRATCH = 4;    // per-CTA scratch sets: launches on different internal streams (nns_chorin_fd_step_host) may overlap
 
 // named barrier ids (0 is __syncthreads)
 enum { BAR_SOR = 1, BAR_ST = 2, BAR_READY = 3, BAR_CONSUMED = 5, BAR_DONE = 7 };   // +0/+1 by member parity
@@ -686,6 +687,7 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
 }
 
 
+#ifdef NNS_ENABLE_WAVE      // experiment of round 1: not reproducible bit for bit, not part of the product build
 // ----------------------------------------------------------------------------------------------
 // Wave kernel: the same two roles, but the SOR wavefront runs CONTINUOUSLY across the members of a CTA.
 //
@@ -1014,6 +1016,8 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_wave_kernel(const St
     if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
+#endif  // NNS_ENABLE_WAVE
+
 using Cfg128 = CfgX<9, 7, 14, 18>;      // 128 x 128: 126 = 14*9 = 18*7, 252 blocks of 63 cells
 
 struct StreamPlan {
@@ -1169,14 +1173,14 @@ int chorin_stream_step(nns_handle *h, const double *uc, const double *vc, const 
             NNS_CUDA(cudaMemset(pl->d_prof, 0, sizeof(long long) * NPROF * h->sm_count));
         }
         pl->grid = h->sm_count;
-        NNS_CUDA(cudaMalloc(&pl->d_img, sizeof(double2) * C::NCH * NT_SOR * (size_t)pl->grid));
-        NNS_CUDA(cudaMemset(pl->d_img, 0, sizeof(double2) * C::NCH * NT_SOR * (size_t)pl->grid));
+        NNS_CUDA(cudaMalloc(&pl->d_img, sizeof(double2) * C::NCH * NT_SOR * (size_t)pl->grid * N_SCRATCH));
+        NNS_CUDA(cudaMemset(pl->d_img, 0, sizeof(double2) * C::NCH * NT_SOR * (size_t)pl->grid * N_SCRATCH));
         NNS_CUDA(cudaFuncSetAttribute(chorin_stream_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)C::SMEM_BYTES));
-        // wave kernel (continuous wavefront, C' in Tensor Memory): opt-in with NNS_STREAM_MODE=wave while it is not faster
-        // than the member-at-a-time kernel (4.87 vs 4.60 ms/step on the 4096-member ensemble)
+#ifdef NNS_ENABLE_WAVE
         const char *mode = getenv("NNS_STREAM_MODE");
         pl->wave = mode && strcmp(mode, "wave") == 0 && h->g.nit - 1 <= 64;
+        if (pl->wave) fprintf(stderr, "[nns_b200] WARNING: NNS_STREAM_MODE=wave selects an experimental kernel whose results are not reproducible bit for bit\n");
         if (pl->wave && getenv("NNS_WAVE_TRACE")) {
             NNS_CUDA(cudaMalloc(&pl->d_trace, sizeof(long long) * NW_SOR * 16 * 4));
             NNS_CUDA(cudaMemset(pl->d_trace, 0, sizeof(long long) * NW_SOR * 16 * 4));
@@ -1190,6 +1194,7 @@ int chorin_stream_step(nns_handle *h, const double *uc, const double *vc, const 
             NNS_CUDA(cudaFuncSetAttribute(chorin_wave_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)WaveSmem<C>::SMEM_BYTES));
         }
+#endif
     }
     StreamArgs a{};
     a.g = h->g;
@@ -1202,7 +1207,7 @@ int chorin_stream_step(nns_handle *h, const double *uc, const double *vc, const 
     a.desc = static_cast<const SBlock *>(pl->d_tab);
     a.tidmap = reinterpret_cast<const short *>(static_cast<const char *>(pl->d_tab) + sizeof(SBlock) * pl->desc.size());
     a.uc = uc; a.vc = vc; a.up = up; a.vp = vp; a.un = un; a.vn = vn; a.p = p;
-    a.cimg = pl->d_img;
+    a.cimg = pl->d_img + (size_t)(h->scratch_slot % N_SCRATCH) * 2 * C::NCH * NT_SOR * (size_t)pl->grid;     // a set per internal stream: concurrent launches never share a C' image
     a.traj_u = tu; a.traj_v = tv; a.traj_p = tp;
     a.traj_member_stride = traj_member_stride; a.traj_off = traj_off;
     a.sweeps = sweeps;
@@ -1210,6 +1215,7 @@ int chorin_stream_step(nns_handle *h, const double *uc, const double *vc, const 
     a.prof = pl->d_prof;
     a.trace = pl->d_trace;
     const int grid = count < pl->grid ? count : pl->grid;
+#ifdef NNS_ENABLE_WAVE
     if (pl->wave) {
         a.redo_count = pl->d_redo;
         a.redo_list = pl->d_redo + 1;
@@ -1228,6 +1234,7 @@ int chorin_stream_step(nns_handle *h, const double *uc, const double *vc, const 
         h->launches += 2;
         return NNS_OK;
     }
+#endif
     chorin_stream_kernel<C, false><<<grid, NT_SOR + NT_ST, C::SMEM_BYTES, st>>>(a);
     NNS_CUDA(cudaGetLastError());
     h->launches += 1;

@@ -37,6 +37,9 @@ struct nns_handle {
     double *d_bcval;          // [batch][n_bcs] or nullptr
     double *d_scratch[4];     // rotation / ui,vi workspace, [batch][nx][ny] each, lazily allocated
     double *d_stage[7];       // device staging of the host-buffer entry points
+    void *d_pool[10];         // cached device buffers of the *_run_host entry points (fields, trajectories, sweeps)
+    size_t pool_bytes[10];
+    int scratch_slot;         // chorin_fd stream path: which of its 4 per-CTA scratch sets the next launch uses (one per internal stream)
     cudaStream_t streams[4];  // copy/compute pipelining of the host-buffer entry points
     void *chip_plan;          // chorin_fd chip path: cached ChipPlan (host) and block table (device)
     void *d_blockdesc;

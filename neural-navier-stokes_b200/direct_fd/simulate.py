@@ -24,8 +24,17 @@ class NavierStokesSystem():
         self.nit, self.rho, self.nu = nit, rho, nu
         self._handle = None
 
+    def _key(self):
+        bcs = tuple((bc.type, bc.boundary, float(bc.value)) for lst in (self.u_bc, self.v_bc, self.p_bc) for bc in lst)
+        return (self.nx, self.ny, self.nit, self.dt, self.rho, self.nu, bcs)
+
     def _h(self):
+        # the reference reads its attributes at every step: rebuild the device handle when they have changed
+        if self._handle is not None and self._handle_key != self._key():
+            self._handle.close()
+            self._handle = None
         if self._handle is None:
+            self._handle_key = self._key()
             self._handle = _lib.Handle(_lib.SOLVER_DIRECT_FD, self.nx, self.ny, self.nit, self.dt, self.rho,
                                        self.nu, batch=1, u_bc=self.u_bc, v_bc=self.v_bc, p_bc=self.p_bc)
         return self._handle

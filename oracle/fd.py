@@ -163,7 +163,7 @@ def chorin_ensemble_run(u, v, u1, v1, p, u_bcs, v_bcs, p_bcs, *, nt, nit, dt, rh
     for a in (u, v, u1, v1, p):
         assert a.dtype == np.float64 and a.flags.c_contiguous
     if threads:
-        os.environ["OMP_NUM_THREADS"] = str(threads)
+        set_threads(threads)
     used = lib().orc_chorin_ensemble_run(C.byref(P), _dp(nu_arr), ua, va, pa, B, nt,
                                          _dp(u), _dp(v), _dp(u1), _dp(v1), _dp(p), _ip(sw))
     return sw, used
@@ -210,3 +210,18 @@ def direct_ensemble_run(u, v, p, u_bcs, v_bcs, p_bcs, *, nt, nit, dt, rho, nu):
 
 def max_threads():
     return lib().orc_max_threads()
+
+
+def host_cores():
+    """Cores this process may use (cgroup / affinity aware), whatever OMP_NUM_THREADS says."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def set_threads(n=None):
+    """Use n OpenMP threads (default: every core of the host) in the following calls; returns n."""
+    n = int(n or host_cores())
+    lib().orc_set_threads(n)
+    return n

@@ -473,6 +473,15 @@ int orc_direct_ensemble_run(const orc_direct_params *P, const double *nu, const 
     return used;
 }
 
+/* Set the OpenMP team size explicitly (torch.distributed.run exports OMP_NUM_THREADS=1 to its workers). */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -5,7 +5,7 @@ NX=NY=128; dx=dy=2./(NX-1)
 B=int(sys.argv[1]) if len(sys.argv)>1 else 333
 lid, nu = cavity_ensemble_params(B, seed=11)
 u_bc, v_bc, p_bc = cavity_bcs(dx, dy)
-os.environ.setdefault("NNS_STREAM_MODE","legacy")
+
 runs=[]
 for rep in range(6):
     ens = ChorinEnsemble(B, NX, NY, u_bc=u_bc, v_bc=v_bc, p_bc=p_bc, nit=50, dt=2e-4, rho=1, nu=nu, beta=1.25, method="explicit", bc_values=cavity_bc_values(lid))

@@ -137,65 +137,63 @@ def test_stream_equals_member_kernel(monkeypatch):
         assert float((x - y).norm() / y.norm()) <= 1e-13
 
 
-def _run_mode(monkeypatch, mode, B, steps, **kw):
+def _run_once(monkeypatch, B, steps, seed=11):
     import torch
     from nns_b200.ensemble import cavity_bcs, cavity_ensemble_params
     monkeypatch.delenv("NNS_CHIP_MODE", raising=False)
-    monkeypatch.setenv("NNS_STREAM_MODE", mode)
-    lid, nu = cavity_ensemble_params(B, seed=11)
-    if "lid" in kw:
-        lid = kw.pop("lid")
-        nu = np.full(len(lid), 0.1)
+    lid, nu = cavity_ensemble_params(B, seed=seed)
     dx = dy = 2. / (NX - 1)
     u_bc, v_bc, p_bc = cavity_bcs(dx, dy)
-    ens = _ens(B, u_bc, v_bc, p_bc, nu, lid, **kw)
+    ens = _ens(B, u_bc, v_bc, p_bc, nu, lid)
     ens.init_variables()
     sw = []
     for _ in range(steps):
         ens.step()
         sw.append(ens.sweeps.clone())
-    return ens.u.clone(), ens.v.clone(), ens.p.clone(), torch.stack(sw), ens.launches
+    return ens.u.clone(), ens.v.clone(), ens.p.clone(), torch.stack(sw)
 
 
-def test_wave_kernel_equals_member_at_a_time_kernel(monkeypatch):
-    """The wave kernel (continuous SOR wavefront over the members of a CTA, right-hand side in Tensor Memory,
-    NNS_STREAM_MODE=wave) executes the same operations per cell in the same order as the member-at-a-time
-    kernel: sweep counts equal and u, v, p equal to rounding (<= 1e-13 relative L2 per member; normally bit for
-    bit -- scripts/determinism_check.py once saw one member of 24 576 differ by a few ulps between two wave
-    runs, which is not understood yet and is why the wave kernel is opt-in), with several members per CTA and a
-    ragged tail."""
+def test_stream_kernel_is_bit_reproducible(monkeypatch):
+    """Two runs of the same ensemble (several members per persistent CTA, ragged tail, 3 steps) agree bit for bit:
+    the named-barrier / halo-slot hand-offs of the warp-specialised kernel leave no run-to-run freedom
+    (scripts/determinism_check.py is the long version: 12+ runs x 4096 members)."""
     import torch
-    a = _run_mode(monkeypatch, "wave", 333, 3)
-    b = _run_mode(monkeypatch, "legacy", 333, 3)
-    assert a[4] > b[4]                       # the wave path really ran (it adds the re-run launch)
-    assert torch.equal(a[3], b[3]) and int(a[3].min()) == 49
-    for x, y in zip(a[:3], b[:3]):
-        err = (x - y).flatten(1).norm(dim=1) / y.flatten(1).norm(dim=1).clamp_min(1e-300)
-        assert float(err.max()) <= 1e-13
+    a = _run_once(monkeypatch, 1200, 3)
+    b = _run_once(monkeypatch, 1200, 3)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
 
 
-def test_wave_kernel_early_exit_members_take_the_rerun_pass(oracle_fd, monkeypatch):
-    """Members whose SOR loop stops before nit - 1 sweeps are detected from the exit flags of the pipelined
-    pass, left untouched and re-run by the member-at-a-time kernel with the exact sweep count: sweep counts
-    and fields vs the oracle, next to members that run all 49 sweeps in the same launch."""
-    lid = np.array([3e-7, 1e-6, 2e-6, 1e-5, 1e-4, 1.0])
-    u, v, p, sw, _ = _run_mode(monkeypatch, "wave", len(lid), 3, lid=lid)
-    from nns_b200.ensemble import cavity_bcs
+@pytest.mark.parametrize("B", [300, 1200])
+def test_step_host_chunked_pipeline_matches_device_step(monkeypatch, B):
+    """nns_chorin_fd_step_host on the 128 x 128 stream path: the batch is cut into 2 (296 <= B < 1184) or 8
+    (B >= 1184) member chunks whose launches run on 4 internal streams and may overlap; every chunk has its own
+    scratch set, so the result equals the one-launch device-resident step bit for bit (3 steps, host roles rotated
+    as bench.py does)."""
+    import torch
+    from nns_b200 import _lib
+    from nns_b200.ensemble import cavity_bcs, cavity_ensemble_params
+    monkeypatch.delenv("NNS_CHIP_MODE", raising=False)
+    lid, nu = cavity_ensemble_params(B, seed=3)
     dx = dy = 2. / (NX - 1)
     u_bc, v_bc, p_bc = cavity_bcs(dx, dy)
-    z = np.zeros((NX, NY))
-    seen = set()
-    for b in range(len(lid)):
-        ub = _bc_tuples(u_bc)
-        ub[1] = ("right", "dirichlet", float(lid[b]))
-        ou, ov, op, osw = oracle_fd.chorin_simulate(z, z, z, ub, _bc_tuples(v_bc), _bc_tuples(p_bc), nt=3, nit=50,
-                                                    dt=2e-4, rho=1, nu=0.1, beta=1.25)
-        assert list(sw[:, b].cpu().numpy()) == list(osw)
-        seen.update(int(s) for s in osw)
-        assert rel_l2(u[b].cpu().numpy(), ou[-1]) <= TOL
-        assert rel_l2(v[b].cpu().numpy(), ov[-1]) <= TOL
-        assert rel_l2(p[b].cpu().numpy(), op[-1]) <= TOL
-    assert min(seen) < 49 and max(seen) == 49, seen
+    ens = _ens(B, u_bc, v_bc, p_bc, nu, lid)
+    ens.init_variables()
+    hs = [torch.zeros((B, NX, NY), dtype=torch.float64).pin_memory() for _ in range(7)]
+    hsw = torch.zeros((B,), dtype=torch.int32).pin_memory()
+    for k, src in enumerate((ens.u, ens.v, ens.u1, ens.v1, ens.p)):
+        hs[k].copy_(src)
+    torch.cuda.synchronize()
+    L = _lib.lib()
+    for _ in range(3):
+        _lib.check(L.nns_chorin_fd_step_host(ens.handle.h, hs[0].data_ptr(), hs[1].data_ptr(), hs[2].data_ptr(),
+                                             hs[3].data_ptr(), hs[4].data_ptr(), hs[5].data_ptr(), hs[6].data_ptr(),
+                                             hsw.data_ptr()))
+        hs[2], hs[0], hs[5] = hs[0], hs[5], hs[2]
+        hs[3], hs[1], hs[6] = hs[1], hs[6], hs[3]
+        ens.step()
+        assert torch.equal(hs[0], ens.u.cpu()) and torch.equal(hs[1], ens.v.cpu()) and torch.equal(hs[4], ens.p.cpu())
+        assert torch.equal(hsw, ens.sweeps.cpu())
 
 
 def test_full_size_ensemble_4096_members(oracle_fd, monkeypatch):
@@ -205,7 +203,6 @@ def test_full_size_ensemble_4096_members(oracle_fd, monkeypatch):
     persistent CTA and position in its queue they land on)."""
     import torch
     monkeypatch.delenv("NNS_CHIP_MODE", raising=False)
-    monkeypatch.delenv("NNS_STREAM_MODE", raising=False)
     from nns_b200.ensemble import cavity_bcs, cavity_ensemble_params
     B = 4096
     lid, nu = cavity_ensemble_params(B, seed=0)
