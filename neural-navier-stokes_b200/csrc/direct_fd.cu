@@ -9,8 +9,17 @@
 //   * "chip": one CTA per member, p (ping-pong) and b resident in shared memory, all nit
 //     sweeps + BCs + velocity update fused in one launch per run of nsteps (small grids,
 //     ensembles).
+//   * "cluster": one thread-block CLUSTER per member (2 .. 16 CTAs): every CTA keeps a band of rows of p (ping-pong)
+//     and b in its shared memory for the whole run, the band edges travel to the neighbouring CTAs through
+//     distributed shared memory after every sweep (one cluster barrier per sweep), RHS and velocity update are fused
+//     around the sweeps and all nsteps run in ONE launch: the Jacobi sweeps are temporally blocked on chip, HBM only
+//     sees u, v once per step (256 x 256: ~103 launches and 2 x 50 passes over p per step before).
 //   * "stream": fields in HBM, one launch per sweep (any grid size).
+#include <cooperative_groups.h>
+
 #include "nns_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace nns {
 
@@ -148,6 +157,221 @@ __global__ void __launch_bounds__(1024, 1) direct_chip_kernel(const DirectArgs a
         for (size_t q = tid; q < N; q += blockDim.x) { ug[q] = us[q]; vg[q] = vs[q]; }
 }
 
+// ---- cluster path -----------------------------------------------------------------------
+// Rows [i0, i1) of the member belong to this CTA; shared-memory row index li = i - i0 + 1 (li = 0 and li = nloc + 1
+// are the halo rows owned by the neighbouring CTAs).  smem: P0, P1, Bs of (band + 2) * pitch doubles each.
+__device__ __forceinline__ void band_apply_bc_smem(double *A, int nx, int ny, int pitch, int i0, int i1, const BcList &L,
+                                                   const double *bcval, double dx, double dy) {
+    const int nloc = i1 - i0;
+    for (int k = 0; k < L.n; ++k) {
+        const double g = bcval ? bcval[L.slot[k]] : L.value[k];
+        const int side = L.side[k];
+        const bool neu = L.type[k] == NNS_BC_NEUMANN;
+        if (side == NNS_SIDE_LEFT) {
+            if (i0 == 0)
+                for (int j = threadIdx.x; j < ny; j += blockDim.x) A[1 * pitch + j] = neu ? A[2 * pitch + j] - dx * g : g;
+        } else if (side == NNS_SIDE_RIGHT) {
+            if (i1 == nx)
+                for (int j = threadIdx.x; j < ny; j += blockDim.x) A[nloc * pitch + j] = neu ? A[(nloc - 1) * pitch + j] + dx * g : g;
+        } else {
+            const int j = side == NNS_SIDE_BOTTOM ? 0 : ny - 1, jn = side == NNS_SIDE_BOTTOM ? 1 : ny - 2;
+            const double sg = side == NNS_SIDE_BOTTOM ? -dy : dy;
+            for (int li = 1 + threadIdx.x; li <= nloc; li += blockDim.x) A[li * pitch + j] = neu ? A[li * pitch + jn] + sg * g : g;
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void band_apply_bc_global(double *A, int nx, int ny, int i0, int i1, const BcList &L,
+                                                     const double *bcval, double dx, double dy) {
+    for (int k = 0; k < L.n; ++k) {
+        const double g = bcval ? bcval[L.slot[k]] : L.value[k];
+        const int side = L.side[k];
+        const bool neu = L.type[k] == NNS_BC_NEUMANN;
+        if (side == NNS_SIDE_LEFT) {
+            if (i0 == 0)
+                for (int j = threadIdx.x; j < ny; j += blockDim.x) A[j] = neu ? A[(size_t)ny + j] - dx * g : g;
+        } else if (side == NNS_SIDE_RIGHT) {
+            if (i1 == nx)
+                for (int j = threadIdx.x; j < ny; j += blockDim.x)
+                    A[(size_t)(nx - 1) * ny + j] = neu ? A[(size_t)(nx - 2) * ny + j] + dx * g : g;
+        } else {
+            const int j = side == NNS_SIDE_BOTTOM ? 0 : ny - 1, jn = side == NNS_SIDE_BOTTOM ? 1 : ny - 2;
+            const double sg = side == NNS_SIDE_BOTTOM ? -dy : dy;
+            for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) A[(size_t)i * ny + j] = neu ? A[(size_t)i * ny + jn] + sg * g : g;
+        }
+        __syncthreads();
+    }
+}
+
+// Point-to-point hand-off between neighbouring CTAs of the cluster: the producer's threads store the band edge into the
+// consumer's shared memory, thread 0 then arrives (release, cluster scope) on the consumer's mbarrier; the consumer's
+// threads wait on their own mbarrier (acquire, cluster scope).  A full cluster barrier per sweep costs several times more.
+__device__ __forceinline__ uint32_t dsm_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void remote_arrive(const void *local_bar, unsigned rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(dsm_u32(local_bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ void cluster_wait(const void *bar, uint32_t parity) {
+    unsigned spins = 0;
+    uint32_t ok = 0;
+    do {
+        asm volatile(
+            "{\n.reg .pred P1;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, P1;\n}"
+            : "=r"(ok) : "r"(dsm_u32(bar)), "r"(parity), "r"(100000u) : "memory");
+        if (!ok && ++spins > (1u << 16)) __trap();       // a stuck cluster traps instead of hanging the GPU
+    } while (!ok);
+}
+
+__global__ void __launch_bounds__(1024, 1) direct_cluster_kernel(const DirectArgs a, int band) {
+    extern __shared__ double smem[];
+    __shared__ __align__(8) unsigned long long hbar[2];       // [0]: the CTA above has delivered my upper halo row, [1]: the CTA below my lower one
+    cg::cluster_group cluster = cg::this_cluster();
+    const int NC = (int)cluster.num_blocks(), r = (int)cluster.block_rank();
+    const int nx = a.g.nx, ny = a.g.ny, pitch = ny | 1;
+    const size_t N = (size_t)nx * ny;
+    const int b = blockIdx.x / NC, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int i0 = r * band, i1 = min(nx, i0 + band), nloc = i1 - i0;
+    const size_t plane = (size_t)(band + 2) * pitch;
+    double *Pc = smem, *Pn = smem + plane, *Bs = smem + 2 * plane;
+    const double dt = a.g.dt, dx = a.g.dx, dy = a.g.dy, rho = a.g.rho;
+    const double nu = a.nu_b ? a.nu_b[b] : a.g.nu;
+    const double *bcval = a.bcval ? a.bcval + (size_t)b * a.n_bcs : nullptr;
+    const double dx2 = dx * dx, dy2 = dy * dy;
+    const double rden = 1.0 / (2.0 * (dx2 + dy2));
+    const double cx = dy2 * rden, cy = dx2 * rden, kb = dx2 * dy2 * rden;
+    const double r2dx = 1.0 / (2.0 * dx), r2dy = 1.0 / (2.0 * dy), rdt = 1.0 / dt;
+    double *ug = a.u + (size_t)b * N, *vg = a.v + (size_t)b * N, *pg = a.p + (size_t)b * N;
+    double *us = a.su + (size_t)b * N, *vs = a.sv + (size_t)b * N;
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dsm_u32(&hbar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dsm_u32(&hbar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster.sync();            // every CTA's mbarriers exist before the first remote arrival
+    uint32_t hpar = 0;
+    const bool has_above = r > 0, has_below = r < NC - 1;
+    // own rows and the two halo rows of p from global memory
+    for (int li = warp; li < nloc + 2; li += nwarps) {
+        const int i = i0 + li - 1;
+        for (int j = lane; j < ny; j += 32) Pc[li * pitch + j] = (i >= 0 && i < nx) ? pg[(size_t)i * ny + j] : 0.0;
+    }
+    __syncthreads();
+
+    for (int n = 0; n < a.nsteps; ++n) {
+        const double *uo = (n & 1) ? us : ug, *vo = (n & 1) ? vs : vg;   // u^n, v^n
+        double *un = (n & 1) ? ug : us, *vn = (n & 1) ? vg : vs;         // u^{n+1}
+        // RHS b of the own rows (direct_fd:56-66)
+        for (int li = 1 + warp; li <= nloc; li += nwarps) {
+            const int i = i0 + li - 1;
+            for (int j = lane; j < ny; j += 32) {
+                double bb = 0.0;
+                if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1) {
+                    const size_t q = (size_t)i * ny + j;
+                    const double ux = (uo[q + 1] - uo[q - 1]) * r2dx, vy = (vo[q + ny] - vo[q - ny]) * r2dy;
+                    const double uy = (uo[q + ny] - uo[q - ny]) * r2dy, vx = (vo[q + 1] - vo[q - 1]) * r2dx;
+                    bb = rho * (rdt * (ux + vy)) - ux * ux - 2.0 * (uy * vx) - vy * vy;
+                }
+                Bs[li * pitch + j] = kb * bb;
+            }
+        }
+        __syncthreads();
+        // exactly nit Jacobi sweeps, p BCs after every sweep (direct_fd:76-86), band edges to the neighbours after the BCs
+        for (int s = 0; s < a.g.nit; ++s) {
+            for (int li = 1 + warp; li <= nloc; li += nwarps) {
+                const int i = i0 + li - 1;
+                for (int j = lane; j < ny; j += 32) {
+                    const int q = li * pitch + j;
+                    double rr = Pc[q];
+                    if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1)
+                        rr = (Pc[q + 1] + Pc[q - 1]) * cx + (Pc[q + pitch] + Pc[q - pitch]) * cy - Bs[q];
+                    Pn[q] = rr;
+                }
+            }
+            __syncthreads();
+            band_apply_bc_smem(Pn, nx, ny, pitch, i0, i1, a.pbc, bcval, dx, dy);
+            if (has_above) {          // my first row is the lower halo row (li = band + 1) of the CTA above
+                double *rem = cluster.map_shared_rank(Pn, r - 1);
+                for (int j = tid; j < ny; j += blockDim.x) rem[(band + 1) * pitch + j] = Pn[1 * pitch + j];
+            }
+            if (has_below) {          // my last row is the upper halo row (li = 0) of the CTA below
+                double *rem = cluster.map_shared_rank(Pn, r + 1);
+                for (int j = tid; j < ny; j += blockDim.x) rem[j] = Pn[nloc * pitch + j];
+            }
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                if (has_above) remote_arrive(&hbar[1], (unsigned)(r - 1));     // I am the CTA below of r - 1
+                if (has_below) remote_arrive(&hbar[0], (unsigned)(r + 1));
+            }
+            // The neighbours' edges of this sweep in my halo rows of Pn.  (They overwrite the buffer I read as Pc one
+            // sweep ago: a neighbour only gets there after my arrival of that sweep, i.e. after those reads.)
+            if (tid == 0) {           // one thread acquires at cluster scope, the CTA barrier passes it on
+                if (has_above) cluster_wait(&hbar[0], hpar);
+                if (has_below) cluster_wait(&hbar[1], hpar);
+            }
+            __syncthreads();
+            hpar ^= 1u;
+            double *t = Pc; Pc = Pn; Pn = t;
+        }
+        // velocity update of the own rows (direct_fd:98-118), then u/v BCs (:121-125)
+        const double kpx = dt / (2.0 * rho * dx), kpy = dt / (2.0 * rho * dy);
+        const double kdx = dt / dx2, kdy = dt / dy2, ax = dt / dx, ay = dt / dy;
+        for (int li = 1 + warp; li <= nloc; li += nwarps) {
+            const int i = i0 + li - 1;
+            for (int j = lane; j < ny; j += 32) {
+                const size_t q = (size_t)i * ny + j;
+                const double uc = uo[q], vc = vo[q];
+                double ru = uc, rv = vc;
+                if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1) {
+                    const int sq = li * pitch + j;
+                    const double uW = uo[q - 1], uE = uo[q + 1], uN = uo[q - ny], uS = uo[q + ny];
+                    const double vW = vo[q - 1], vE = vo[q + 1], vN = vo[q - ny], vS = vo[q + ny];
+                    ru = uc - uc * ax * (uc - uW) - vc * ay * (uc - uN) - kpx * (Pc[sq + 1] - Pc[sq - 1]) +
+                         nu * (kdx * (uE - 2.0 * uc + uW) + kdy * (uS - 2.0 * uc + uN));
+                    rv = vc - uc * ax * (vc - vW) - vc * ay * (vc - vN) - kpy * (Pc[sq + pitch] - Pc[sq - pitch]) +
+                         nu * (kdx * (vE - 2.0 * vc + vW) + kdy * (vS - 2.0 * vc + vN));
+                }
+                un[q] = ru;
+                vn[q] = rv;
+            }
+        }
+        __syncthreads();
+        band_apply_bc_global(un, nx, ny, i0, i1, a.ubc, bcval, dx, dy);
+        band_apply_bc_global(vn, nx, ny, i0, i1, a.vbc, bcval, dx, dy);
+        if (a.traj_u || (a.flags & NNS_FLAG_CHECK_FINITE)) {
+            const size_t toff = ((size_t)b * a.nsteps_total + (a.step0 + n)) * N;
+            unsigned long long bad = 0;
+            for (int li = 1 + warp; li <= nloc; li += nwarps) {
+                const int i = i0 + li - 1;
+                for (int j = lane; j < ny; j += 32) {
+                    const size_t q = (size_t)i * ny + j;
+                    const double x = un[q], y = vn[q], z = Pc[li * pitch + j];
+                    if (a.traj_u) { a.traj_u[toff + q] = x; a.traj_v[toff + q] = y; a.traj_p[toff + q] = z; }
+                    bad += !(isfinite(x) && isfinite(y) && isfinite(z));
+                }
+            }
+            if ((a.flags & NNS_FLAG_CHECK_FINITE) && bad) atomicAdd(a.nonfinite, bad);
+        }
+        // the neighbouring CTAs read my rows of u^{n+1}, v^{n+1} (global memory) in their next RHS / update
+        __threadfence();
+        cluster.sync();
+    }
+    for (int li = 1 + warp; li <= nloc; li += nwarps) {
+        const int i = i0 + li - 1;
+        for (int j = lane; j < ny; j += 32) pg[(size_t)i * ny + j] = Pc[li * pitch + j];
+    }
+    if (a.nsteps & 1)
+        for (int li = 1 + warp; li <= nloc; li += nwarps) {
+            const int i = i0 + li - 1;
+            for (int j = lane; j < ny; j += 32) { const size_t q = (size_t)i * ny + j; ug[q] = us[q]; vg[q] = vs[q]; }
+        }
+}
+
 // ---- stream path ------------------------------------------------------------------------
 __global__ void direct_rhs_kernel(const double *__restrict__ u, const double *__restrict__ v,
                                   double *__restrict__ bout, Geometry g) {
@@ -248,7 +472,9 @@ int direct_run(nns_handle *h, double *u, double *v, double *p, int nsteps, doubl
     if ((rc = ensure(&h->d_scratch[0], bytes)) || (rc = ensure(&h->d_scratch[1], bytes))) return rc;
     const int pitch = g.ny | 1;
     const size_t smem = sizeof(double) * 3 * (size_t)g.nx * pitch;
-    if (smem <= (size_t)h->max_smem_optin) {
+    const char *dmode = getenv("NNS_DIRECT_MODE");          // tests: "cluster" / "stream" skip the earlier paths
+    const bool skip_chip = dmode && (strcmp(dmode, "cluster") == 0 || strcmp(dmode, "stream") == 0);
+    if (smem <= (size_t)h->max_smem_optin && !skip_chip) {
         DirectArgs a{};
         a.g = g; a.ubc = h->bc[0]; a.vbc = h->bc[1]; a.pbc = h->bc[2];
         a.nu_b = h->d_nu; a.bcval = h->d_bcval; a.n_bcs = h->n_bcs;
@@ -262,6 +488,44 @@ int direct_run(nns_handle *h, double *u, double *v, double *p, int nsteps, doubl
         NNS_CUDA(cudaGetLastError());
         h->launches += 1;
         return NNS_OK;
+    }
+    // cluster path: row bands of one member over the CTAs of a thread-block cluster
+    if (!(dmode && strcmp(dmode, "stream") == 0)) {
+        // the sweeps are bound by shared-memory bandwidth: the largest cluster whose bands still have >= 8 rows, else
+        // the largest one that fits at all
+        for (int pass = 0; pass < 2; ++pass)
+        for (int nc = 16; nc >= 2; nc /= 2) {
+            const int band = (g.nx + nc - 1) / nc;
+            const size_t csmem = sizeof(double) * 3 * (size_t)(band + 2) * pitch;
+            if (band < (pass == 0 ? 8 : 2) || g.nx - (nc - 1) * band < 2 || csmem > (size_t)h->max_smem_optin) continue;
+            DirectArgs a{};
+            a.g = g; a.ubc = h->bc[0]; a.vbc = h->bc[1]; a.pbc = h->bc[2];
+            a.nu_b = h->d_nu; a.bcval = h->d_bcval; a.n_bcs = h->n_bcs;
+            a.nsteps = nsteps; a.nsteps_total = nsteps; a.step0 = 0; a.flags = h->params.flags;
+            a.u = u; a.v = v; a.p = p; a.su = h->d_scratch[0]; a.sv = h->d_scratch[1];
+            a.traj_u = tu; a.traj_v = tv; a.traj_p = tp; a.nonfinite = h->d_nonfinite;
+            NNS_CUDA(cudaFuncSetAttribute(direct_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+            if (nc > 8) NNS_CUDA(cudaFuncSetAttribute(direct_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(g.batch * nc));
+            const char *thr = getenv("NNS_DIRECT_THREADS");        // experiments
+            cfg.blockDim = dim3(thr ? (unsigned)atoi(thr) : 512u);
+            cfg.dynamicSmemBytes = csmem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)nc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, direct_cluster_kernel, &cfg) != cudaSuccess || nclusters < 1) {
+                cudaGetLastError();
+                continue;           // this cluster size cannot be scheduled on the device: try the next one / the stream path
+            }
+            NNS_CUDA(cudaLaunchKernelEx(&cfg, direct_cluster_kernel, a, band));
+            h->launches += 1;
+            return NNS_OK;
+        }
     }
     // stream path
     if ((rc = ensure(&h->d_b, bytes)) || (rc = ensure(&h->d_p2, bytes))) return rc;

@@ -58,23 +58,43 @@ def test_direct_step_in_place(oracle_fd):
     assert rel_l2(u, ou) <= TOL and rel_l2(v, ov) <= TOL and rel_l2(p, op) <= TOL
 
 
-def test_direct_chip_equals_stream_path(oracle_fd):
-    """Same inputs through both code paths (chip: grid in smem; stream: HBM) for an odd nit,
-    plus a batch with per-member nu."""
+@pytest.mark.parametrize("shape", [(40, 36), (72, 60), (33, 130)])
+def test_direct_chip_cluster_and_stream_paths_agree(oracle_fd, monkeypatch, shape):
+    """The same inputs through the three code paths -- chip (member in one SM's shared memory), cluster (row bands
+    over a thread-block cluster, halo rows through distributed shared memory) and stream (one launch per sweep) --
+    for an odd nit, an odd number of steps, mixed BC order and a batch with per-member nu: each against the oracle
+    (rel-L2 <= 1e-10) and against each other (same expression per cell up to the compiler's FMA contraction: rel-L2 <= 1e-13)."""
     import torch
-    from nns_b200.ensemble import DirectEnsemble, cavity_bcs
-    from nns_b200 import _lib
-    B, nx, ny = 4, 40, 36
+    import nns_b200
+    from nns_b200.ensemble import DirectEnsemble
+    D, Nm = nns_b200.DirichletBoundaryCondition, nns_b200.NeumannBoundaryCondition
+    B = 3
+    nx, ny = shape
     dx, dy = 2. / (nx - 1), 2. / (ny - 1)
-    u_bc, v_bc, p_bc = cavity_bcs(dx, dy)
-    nus = np.array([0.05, 0.1, 0.02, 0.08])
-    ens = DirectEnsemble(B, nx, ny, u_bc=u_bc, v_bc=v_bc, p_bc=p_bc, nit=7, dt=5e-4, rho=1, nu=nus)
+    u_bc = [D(0.0, 'left', dx, dy), D(1.0, 'right', dx, dy), Nm(0.1, 'top', dx, dy), D(0.0, 'bottom', dx, dy)]
+    v_bc = [D(0.2, 'top', dx, dy), Nm(0.0, 'left', dx, dy), D(0.0, 'right', dx, dy), Nm(-0.1, 'bottom', dx, dy)]
+    p_bc = [D(0.0, 'top', dx, dy), Nm(0.0, 'bottom', dx, dy), Nm(0.3, 'left', dx, dy), Nm(0.0, 'right', dx, dy)]
+    nus = np.array([0.05, 0.1, 0.02])
     f = [np.stack([smooth_ic(nx, ny, 40 + 3 * b + k, amp=0.1)[0] for b in range(B)]) for k in range(3)]
-    ens.set_state(*f)
-    tu, tv, tp = ens.run(5, trajectory=True)
-    torch.cuda.synchronize()
+    out = {}
+    for mode in ("chip", "cluster", "stream"):
+        monkeypatch.setenv("NNS_DIRECT_MODE", mode)
+        ens = DirectEnsemble(B, nx, ny, u_bc=u_bc, v_bc=v_bc, p_bc=p_bc, nit=7, dt=2e-4, rho=1.1, nu=nus)
+        ens.set_state(*f)
+        tu, tv, tp = ens.run(5, trajectory=True)
+        torch.cuda.synchronize()
+        out[mode] = (tu.clone(), tv.clone(), tp.clone(), ens.u.clone(), ens.v.clone(), ens.p.clone(), ens.launches)
+    monkeypatch.delenv("NNS_DIRECT_MODE")
+    assert out["chip"][6] == 1 and out["cluster"][6] == 1 and out["stream"][6] > 50     # the three paths really ran
     for b in range(B):
-        u, v, p = oracle_fd.direct_simulate(f[0][b], f[1][b], f[2][b], u_bc, v_bc, p_bc, nt=5, nit=7, dt=5e-4,
-                                            rho=1, nu=nus[b])
-        assert rel_l2(tu[b].cpu().numpy(), u) <= TOL and rel_l2(tp[b].cpu().numpy(), p) <= TOL
-        assert rel_l2(ens.v[b].cpu().numpy(), v[-1]) <= TOL
+        u, v, p = oracle_fd.direct_simulate(f[0][b], f[1][b], f[2][b], u_bc, v_bc, p_bc, nt=5, nit=7, dt=2e-4,
+                                            rho=1.1, nu=nus[b])
+        for mode in out:
+            tu, tv, tp = out[mode][:3]
+            assert rel_l2(tu[b].cpu().numpy(), u) <= TOL and rel_l2(tv[b].cpu().numpy(), v) <= TOL, mode
+            assert rel_l2(tp[b].cpu().numpy(), p) <= TOL, mode
+            assert rel_l2(out[mode][3][b].cpu().numpy(), u[-1]) <= TOL and rel_l2(out[mode][5][b].cpu().numpy(), p[-1]) <= TOL
+    for k in range(6):
+        for other in ("cluster", "stream"):
+            d = float((out["chip"][k] - out[other][k]).norm() / out["chip"][k].norm())
+            assert d <= 1e-13, (k, other, d)
