@@ -8,9 +8,12 @@
 // differs from the reference.  The device side is a table-driven batched fp64 GEMM kernel
 // (all products of one dependency level in ONE launch) plus a few fused pointwise kernels.
 //
-// Tensor cores: tcgen05 has no f64 kind, and on B200 the legacy DMMA path (mma.sync m8n8k4.f64)
-// has the same peak as the FP64 FMA pipe (NVIDIA quotes 40 TFLOP/s for both), so these
-// 126^3-class products run on DFMA with register tiling; see DESIGN.md.
+// Tensor cores: tcgen05 has no f64 kind; the legacy tensor path mma.sync.aligned.m8n8k4.f64 (SASS DMMA) does, and on
+// B200 it runs on the tensor pipe at 37.1 TFLOP/s against 33.9 TFLOP/s of the FP64 FMA pipe (measured:
+// scripts/micro/dmma_bench.cu, profiles/r2_micro_dmma_bench.txt -- ncu: sm__pipe_tensor_cycles_active 99.99 %,
+// sm__pipe_fp64 idle).  The products are dense contractions, so they run on DMMA: 8 FMAs per lane and instruction
+// from two operand registers, i.e. a quarter of the shared-memory operand traffic of a 4 x 4 register-tiled DFMA
+// kernel, and the FP64 pipe stays free for the pointwise kernels.
 #include "nns_common.cuh"
 
 namespace nns {
@@ -36,61 +39,108 @@ struct GemmTable {
     int n;
 };
 
-constexpr int TM = 32, TN = 32, TK = 16;
+constexpr int TM = 64, TN = 64, TK = 16;
+constexpr int SA = TK + 4, SB = TN + 4;     // shared-memory strides (doubles): conflict-free fragment loads (stride = 4 mod 16)
 
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// 64 x 64 tile per CTA, 8 warps: warp (wy, wx) of a 2 x 4 grid computes 32 x 16 = 4 x 2 DMMA tiles of 8 x 8.
+// m8n8k4 fragments: lane l holds A[l / 4][l % 4], B[l % 4][l / 4], C[l / 4][2 (l % 4) + {0, 1}].
+// The next k-slab travels global -> registers while the current one is multiplied out of shared memory.
 __global__ void __launch_bounds__(256) spectral_gemm_kernel(const GemmTable tab, int batch) {
     const int gi = blockIdx.z / batch, b = blockIdx.z - gi * batch;
     const GemmDesc &d = tab.g[gi];
     const int row0 = blockIdx.y * TM, col0 = blockIdx.x * TN;
     if (row0 >= d.m || col0 >= d.n) return;
-    __shared__ double As[TK][TM + 1];
-    __shared__ double Bs[TK][TN + 1];
+    __shared__ double As[TM * SA];
+    __shared__ double Bs[TK * SB];
     const double *A = d.A + (long long)b * d.sA, *B = d.B + (long long)b * d.sB;
     double *C = d.C + (long long)b * d.sC;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16 threads, 2 x 2 outputs each
-    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-    for (int k0 = 0; k0 < d.k; k0 += TK) {
-        for (int q = threadIdx.x; q < TM * TK; q += 256) {
-            const int r = q / TK, kk = q - r * TK;               // A tile: rows row0.., cols k0..
-            const int gr = row0 + r, gk = k0 + kk;
-            As[kk][r] = (gr < d.m && gk < d.k) ? A[(long long)gr * d.lda + gk] : 0.0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wy = warp >> 2, wx = warp & 3;
+    const int fr = lane >> 2, fk = lane & 3;
+    double acc[4][2][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    double ra[4], rb[4];
+    // A slab: 64 rows x 16 k (thread: row tid / 4, k = 4 (tid % 4) .. +3); B slab: 16 k x 64 cols
+    auto gload = [&](int k0) {
+        {
+            const int r = tid >> 2, kk = (tid & 3) * 4, gr = row0 + r;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int gk = k0 + kk + q;
+                ra[q] = (gr < d.m && gk < d.k) ? A[(long long)gr * d.lda + gk] : 0.0;
+            }
+        }
+        if (d.transB) {       // B stored n x k: thread reads 4 consecutive k of one column
+            const int c = tid >> 2, kk = (tid & 3) * 4, gc = col0 + c;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int gk = k0 + kk + q;
+                rb[q] = (gc < d.n && gk < d.k) ? B[(long long)gc * d.ldb + gk] : 0.0;
+            }
+        } else {              // B stored k x n: thread reads 4 consecutive columns of one k
+            const int kk = tid >> 4, c = (tid & 15) * 4, gk = k0 + kk;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int gc = col0 + c + q;
+                rb[q] = (gc < d.n && gk < d.k) ? B[(long long)gk * d.ldb + gc] : 0.0;
+            }
+        }
+    };
+    auto sstore = [&]() {
+        {
+            const int r = tid >> 2, kk = (tid & 3) * 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) As[r * SA + kk + q] = ra[q];
         }
         if (d.transB) {
-            for (int q = threadIdx.x; q < TN * TK; q += 256) {
-                const int c = q / TK, kk = q - c * TK;           // B stored n x k
-                const int gc = col0 + c, gk = k0 + kk;
-                Bs[kk][c] = (gc < d.n && gk < d.k) ? B[(long long)gc * d.ldb + gk] : 0.0;
-            }
-        } else {
-            for (int q = threadIdx.x; q < TN * TK; q += 256) {
-                const int kk = q / TN, c = q - kk * TN;          // B stored k x n
-                const int gc = col0 + c, gk = k0 + kk;
-                Bs[kk][c] = (gc < d.n && gk < d.k) ? B[(long long)gk * d.ldb + gc] : 0.0;
-            }
-        }
-        __syncthreads();
+            const int c = tid >> 2, kk = (tid & 3) * 4;
 #pragma unroll
-        for (int kk = 0; kk < TK; ++kk) {
-            const double a0 = As[kk][ty], a1 = As[kk][ty + 16];
-            const double b0 = Bs[kk][tx], b1 = Bs[kk][tx + 16];
-            acc[0][0] = fma(a0, b0, acc[0][0]);
-            acc[0][1] = fma(a0, b1, acc[0][1]);
-            acc[1][0] = fma(a1, b0, acc[1][0]);
-            acc[1][1] = fma(a1, b1, acc[1][1]);
+            for (int q = 0; q < 4; ++q) Bs[(kk + q) * SB + c] = rb[q];
+        } else {
+            const int kk = tid >> 4, c = (tid & 15) * 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) Bs[kk * SB + c + q] = rb[q];
         }
+    };
+    gload(0);
+    for (int k0 = 0; k0 < d.k; k0 += TK) {
+        __syncthreads();          // the previous slab has been consumed
+        sstore();
         __syncthreads();
+        if (k0 + TK < d.k) gload(k0 + TK);
+#pragma unroll
+        for (int k4 = 0; k4 < TK; k4 += 4) {
+            double af[4], bf[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = As[(wy * 32 + i * 8 + fr) * SA + k4 + fk];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) bf[j] = Bs[(k4 + fk) * SB + wx * 16 + j * 8 + fr];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
     }
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const int gr = row0 + ty + 16 * r, gc = col0 + tx + 16 * c;
-            if (gr < d.m && gc < d.n) {
-                double v = acc[r][c];
-                if (d.epi == 1) v = v / (d.e0 + d.e1 * d.lx[gr] + d.e2 * d.ly[gc]);
-                C[(long long)gr * d.ldc + gc] = v;
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gr = row0 + wy * 32 + i * 8 + fr, gc = col0 + wx * 16 + j * 8 + 2 * fk + e;
+                if (gr < d.m && gc < d.n) {
+                    double v = acc[i][j][e];
+                    if (d.epi == 1) v = v / (d.e0 + d.e1 * d.lx[gr] + d.e2 * d.ly[gc]);
+                    C[(long long)gr * d.ldc + gc] = v;
+                }
             }
-        }
 }
 
 // F = 2 f - 3dt (u f_x + v f_y) + dt (u1 f1_x + v1 f1_y) + dt (f_xx + f_yy)   (chorin_spectral:277-282)
@@ -204,6 +254,12 @@ struct SpectralPlan {
     double *W;        // 12 derivative planes + scratch, each batch*n*m
     double *scratch[8];
     double *ui, *vi;  // predictor outputs of the run loop
+    // CUDA graph of one full buffer rotation (three steps) of the run loop: a step is a chain of 17 small dependent
+    // launches (126^2 problems), i.e. launch-latency-bound when issued one by one
+    cudaGraphExec_t gexec;
+    cudaStream_t cap;
+    const void *gkey[8];
+    long long gnodes;
 };
 
 static int run_table(nns_handle *h, GemmTable &t, int batch, cudaStream_t st) {
@@ -266,6 +322,8 @@ void spectral_destroy(nns_handle *h) {
     cudaFree(sp->W);
     for (int i = 0; i < 8; ++i) cudaFree(sp->scratch[i]);
     cudaFree(sp->ui); cudaFree(sp->vi);
+    if (sp->gexec) cudaGraphExecDestroy(sp->gexec);
+    if (sp->cap) cudaStreamDestroy(sp->cap);
     delete sp;
     h->spectral = nullptr;
 }
@@ -371,7 +429,45 @@ int spectral_run(nns_handle *h, double *bufU[3], double *bufV[3], double *p, int
     if (!sp->ui) NNS_CUDA(cudaMalloc(&sp->ui, bytes));
     if (!sp->vi) NNS_CUDA(cudaMalloc(&sp->vi, bytes));
     int cur = 0, prev = 1, nxt = 2, rc;
-    for (int n = 0; n < nsteps; ++n) {
+    int n0 = 0;
+    const char *nog = getenv("NNS_SPECTRAL_NOGRAPH");
+    if (!tu && nsteps >= 6 && !(nog && nog[0] == '1')) {
+        // replay whole rotations (3 steps: the buffer roles are back where they started) from a captured graph
+        const void *key[8] = {bufU[0], bufU[1], bufU[2], bufV[0], bufV[1], bufV[2], p, (const void *)(size_t)h->params.flags};
+        if (!sp->gexec || memcmp(key, sp->gkey, sizeof(key)) != 0) {
+            if (sp->gexec) { cudaGraphExecDestroy(sp->gexec); sp->gexec = nullptr; }
+            if (!sp->cap) NNS_CUDA(cudaStreamCreateWithFlags(&sp->cap, cudaStreamNonBlocking));
+            const long long l0 = h->launches;
+            NNS_CUDA(cudaStreamBeginCapture(sp->cap, cudaStreamCaptureModeThreadLocal));
+            int c = 0, pv = 1, nx2 = 2;
+            rc = NNS_OK;
+            for (int k = 0; k < 3 && rc == NNS_OK; ++k) {
+                rc = spectral_predictor(h, bufU[c], bufV[c], bufU[pv], bufV[pv], sp->ui, sp->vi, sp->cap);
+                if (rc == NNS_OK) rc = spectral_correct(h, sp->ui, sp->vi, p, bufU[nx2], bufV[nx2], p, nullptr, sp->cap);
+                if (rc == NNS_OK && (h->params.flags & NNS_FLAG_CHECK_FINITE)) {
+                    spectral_snapshot_kernel<<<dim3(64, sp->batch), 256, 0, sp->cap>>>(bufU[nx2], bufV[nx2], p, nullptr, nullptr, nullptr, N,
+                                                                                    nsteps, 0, h->d_nonfinite, h->params.flags);
+                    h->launches += 1;
+                }
+                const int t = pv; pv = c; c = nx2; nx2 = t;
+            }
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamEndCapture(sp->cap, &graph);
+            sp->gnodes = h->launches - l0;
+            h->launches = l0;
+            if (rc != NNS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) { set_error("chorin_spectral: graph capture failed: %s", cudaGetErrorString(e)); return NNS_ERR_CUDA; }
+            e = cudaGraphInstantiate(&sp->gexec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) { set_error("chorin_spectral: graph instantiation failed: %s", cudaGetErrorString(e)); return NNS_ERR_CUDA; }
+            memcpy(sp->gkey, key, sizeof(key));
+        }
+        const int reps = nsteps / 3;
+        for (int k = 0; k < reps; ++k) NNS_CUDA(cudaGraphLaunch(sp->gexec, st));
+        h->launches += sp->gnodes * reps;
+        n0 = reps * 3;
+    }
+    for (int n = n0; n < nsteps; ++n) {
         if ((rc = spectral_predictor(h, bufU[cur], bufV[cur], bufU[prev], bufV[prev], sp->ui, sp->vi, st))) return rc;
         if ((rc = spectral_correct(h, sp->ui, sp->vi, p, bufU[nxt], bufV[nxt], p, nullptr, st))) return rc;
         if (tu || (h->params.flags & NNS_FLAG_CHECK_FINITE)) {

@@ -166,6 +166,52 @@ class DirectEnsemble(_Ensemble):
         self.run(1)
 
 
+class SpectralEnsemble:
+    """B independent chorin_spectral simulations with the same operators (semantics of
+    src/chorin_spectral/simulate.py per member); device-resident state, ``run`` replays the step chain from a CUDA graph."""
+
+    def __init__(self, batch, nx, ny, *, u_bc, v_bc, dt=0.001, rho=1, nu=1, beta=1.25, nit=50, device=None,
+                 check_finite=False):
+        import ctypes as C
+        from .chorin_spectral.operators import SpectralOperators
+        if not torch.cuda.is_available():
+            raise RuntimeError("nns_b200 ensembles need a CUDA device (no CPU fallback)")
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.batch, self.nx, self.ny = int(batch), int(nx), int(ny)
+        self.ops = SpectralOperators(self.nx, self.ny, u_bc, v_bc)
+        if not self.ops.is_real():
+            raise ValueError("the operators of this size have a complex spectrum (the reference fails too: even N >= 64)")
+        with torch.cuda.device(self.device):
+            self.handle = _lib.Handle(_lib.SOLVER_CHORIN_SPECTRAL, nx, ny, nit, dt, rho, nu, beta=beta, batch=self.batch,
+                                      device=self.device.index, check_finite=check_finite)
+            arrs = self.ops.abi_arrays()
+            ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+            _lib.check(_lib.lib().nns_spectral_set_operators(self.handle.h, ptrs, len(arrs)))
+        self._L = _lib.lib()
+        z = lambda: torch.zeros((self.batch, self.nx, self.ny), dtype=torch.float64, device=self.device)  # noqa: E731
+        self.u, self.v, self.u1, self.v1, self.p = z(), z(), z(), z(), z()
+
+    def set_state(self, u, v, p, u1=None, v1=None):
+        for dst, src in ((self.u, u), (self.v, v), (self.p, p), (self.u1, u if u1 is None else u1),
+                         (self.v1, v if v1 is None else v1)):
+            _Ensemble._to_dev(dst, src)
+
+    def run(self, nsteps, trajectory=False):
+        tu = tv = tp = None
+        if trajectory:
+            tu, tv, tp = (torch.empty((self.batch, nsteps, self.nx, self.ny), dtype=torch.float64,
+                                      device=self.device) for _ in range(3))
+        ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self._L.nns_spectral_run(self.handle.h, self.u.data_ptr(), self.v.data_ptr(), self.u1.data_ptr(),
+                                            self.v1.data_ptr(), self.p.data_ptr(), nsteps, ptr(tu), ptr(tv), ptr(tp), st))
+        return (tu, tv, tp) if trajectory else None
+
+    @property
+    def launches(self):
+        return self.handle.launches
+
+
 def cavity_bcs(dx, dy, lid=1.0):
     """The lid-driven-cavity BC lists of the reference demos (chorin_fd/simulate.py:296-315)."""
     from .boundary import DirichletBoundaryCondition as D, NeumannBoundaryCondition as N
