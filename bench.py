@@ -187,16 +187,14 @@ def run_reference(args, rank, world):
         "gpu_launches": 0}))
 
 
-def run_slab(args, rank, world, local):
-    """One large chorin_fd grid on row slabs (strong scaling): a step = one time step of the whole grid."""
+def slab_measure(workload, steps, warmup, rank, world, local, with_clocks=True):
+    """One large chorin_fd grid on row slabs (strong scaling): a step = one time step of the whole grid.
+    The process group must exist already for world > 1.  Returns the JSON object on rank 0, None elsewhere."""
     import torch
     import torch.distributed as dist
     from nns_b200.ensemble import cavity_bcs
     from nns_b200.slab import SlabChorin
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    nx, ny, nit, dt, nu = SLAB_WORKLOADS[args.workload]
+    nx, ny, nit, dt, nu = SLAB_WORKLOADS[workload]
     dx, dy = 2. / (nx - 1), 2. / (ny - 1)
     u_bc, v_bc, p_bc = cavity_bcs(dx, dy)
     sl = SlabChorin(nx, ny, u_bc=u_bc, v_bc=v_bc, p_bc=p_bc, nit=nit, dt=dt, rho=1, nu=nu, beta=1.25)
@@ -207,52 +205,195 @@ def run_slab(args, rank, world, local):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         sl.step()
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and with_clocks:
         sampler.start()
     l0 = sl.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     sor_ms, sweeps = [], []
-    for _ in range(args.steps):
+    for _ in range(steps):
         sl.step()
         ms, ticks = sl.last_sor_timing()
         sor_ms.append(ms)
         sweeps.append(sl.last_sweeps)
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if rank == 0 and with_clocks else None
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     finite = bool(torch.isfinite(sl.u).all() and torch.isfinite(sl.p).all())
+    mode = "single GPU" if world == 1 else ("peer-memory mailboxes" if sl.p2p else "nccl send/recv")
+    out = None
     if rank == 0:
         peak, peak_src = peaks()
         cells = nx * ny
         kms = float(np.mean(sor_ms)) / ticks          # average sweep-kernel launch (one tick), exchange included for N > 1
         S = float(np.mean(sweeps))
         achieved = BYTES_PER_CELL_SWEEP * (cells / world) * S / ticks / (kms * 1e-3) / 1e9
-        print(json.dumps({
-            "metric": METRIC, "value": cells * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        fused = BYTES_PER_CELL_UPDATE * cells / (ms_total / steps * 1e-3) / 1e9
+        out = {
+            "metric": METRIC, "value": cells * steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "nx": nx, "ny": ny, "nit": nit, "dt": dt, "nu": nu, "beta": 1.25,
-                       "method": "explicit", "parallelism": "row slabs, NCCL send/recv of halo rows per SOR tick",
+            "config": {"workload": workload, "nx": nx, "ny": ny, "nit": nit, "dt": dt, "nu": nu, "beta": 1.25,
+                       "method": "explicit", "parallelism": "row slabs, halo rows of p per SOR tick (NCCL or peer mailboxes)",
+                       "exchange_mode": mode,
                        "l2": "p + C' per GPU %.2f GB >> 126 MB L2" % (2 * cells * 8 / world / 1e9),
                        "sweeps_per_step": [int(min(sweeps)), int(max(sweeps))], "ticks_per_step": int(ticks),
                        "finite": finite},
             "e2e": None, "gpu_launches": int(sl.launches - l0), "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "slab_sweep_kernel",
-                         "bytes_per_cell_sweep": BYTES_PER_CELL_SWEEP, "kernel_ms": kms,
-                         "note": "un-blocked exact-order sweeps: 24 B per cell and sweep; per-tick launch average over "
-                                 "the tick loop of a step (CUDA events inside the library)"}}))
+            "roofline": {"bound": "hbm", "achieved": fused, "peak": peak, "unit": "GB/s", "frac": fused / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "slab step (all kernels of a time step)",
+                         "bytes_per_cell_update": BYTES_PER_CELL_UPDATE,
+                         "sweep_kernel": {"achieved": achieved, "frac": achieved / peak, "kernel_ms": kms,
+                                          "bytes_per_cell_sweep": BYTES_PER_CELL_SWEEP},
+                         "note": "frac: fully fused model (64 B per cell-update); sweep_kernel: the un-blocked exact-order "
+                                 "sweeps as they are implemented (24 B per cell and sweep, per-tick launch average)"}}
+    del sl
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_slab(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    out = slab_measure(args.workload, args.steps, args.warmup, rank, world, local)
+    if rank == 0:
+        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _events_ms(fn):
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+DMMA_PEAK_TFLOPS = 37.09     # measured on B200: scripts/micro/dmma_bench.cu -> profiles/r2_micro_dmma_bench.txt
+
+
+def extra_configs():
+    """The single-simulation configs of BASELINE.json (configs[0..2]) device-resident and device-timed (CUDA events, no
+    trajectory copy), each with its roofline fraction and a CPU baseline (oracle port, bounded sample).  N = 1 only."""
+    import torch
+    import nns_b200
+    from nns_b200.ensemble import ChorinEnsemble, DirectEnsemble, SpectralEnsemble, cavity_bcs
+    from oracle import fd as ofd
+    ofd.build()
+    peak, _ = peaks()
+    out = {}
+    # ---- config 1: chorin_fd cavity 41 x 41, nt = 500, nit = 50 (one 13 KiB problem: latency-bound, one SM)
+    try:
+        nx = ny = 41
+        u_bc, v_bc, p_bc = cavity_bcs(2. / (nx - 1), 2. / (ny - 1))
+        ens = ChorinEnsemble(1, nx, ny, u_bc=u_bc, v_bc=v_bc, p_bc=p_bc, nit=50, dt=1e-3, rho=1, nu=0.1, beta=1.25,
+                             method="explicit")
+        ens.init_variables()
+        ens.run(50)
+        ms = _events_ms(lambda: ens.run(500)) / 500
+        z = np.zeros((nx, ny))
+        ofd.set_threads(1)
+        t0 = time.perf_counter()
+        ofd.chorin_simulate(z, z, z, u_bc, v_bc, p_bc, nt=500, nit=50, dt=1e-3, rho=1, nu=0.1, beta=1.25, method="explicit")
+        tc = time.perf_counter() - t0
+        ach = BYTES_PER_CELL_UPDATE * nx * ny / (ms * 1e-3) / 1e9
+        out["chorin_fd_cavity41"] = {
+            "config": "chorin_fd cavity 41x41, nit=50, dt=1e-3, explicit, steps 50..550 of the run (BASELINE configs[0])",
+            "ms_per_step": ms, "value": nx * ny / (ms * 1e-3), "unit": UNIT, "steps": 500,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "note": "one 13 KiB problem on one SM: latency-bound, not a roofline config"},
+            "cpu_baseline": {"value": nx * ny * 500 / tc, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": "500 steps in %.2f s (oracle/oracle.c)" % tc}}
+        del ens
+    except Exception as exc:
+        out["chorin_fd_cavity41"] = {"error": repr(exc)}
+    # ---- config 2a: direct_fd cavity 256 x 256, nt = 2000, nit = 50, dt = 1e-4 (stable; the shipped 1e-3 is not)
+    try:
+        nx = ny = 256
+        u_bc, v_bc, p_bc = cavity_bcs(2. / (nx - 1), 2. / (ny - 1))
+        ens = DirectEnsemble(1, nx, ny, u_bc=u_bc, v_bc=v_bc, p_bc=p_bc, nit=50, dt=1e-4, rho=1, nu=0.1)
+        ens.run(20)
+        l0 = ens.launches
+        ms = _events_ms(lambda: ens.run(2000)) / 2000
+        launches = ens.launches - l0
+        z = np.zeros((nx, ny))
+        t0 = time.perf_counter()
+        ofd.direct_simulate(z.copy(), z.copy(), z.copy(), u_bc, v_bc, p_bc, nt=40, nit=50, dt=1e-4, rho=1, nu=0.1)
+        tc = time.perf_counter() - t0
+        ach = 48 * nx * ny / (ms * 1e-3) / 1e9
+        out["direct_fd_cavity256"] = {
+            "config": "direct_fd cavity 256x256, nt=2000, nit=50 Jacobi sweeps, dt=1e-4 (BASELINE configs[1], parity variant 2a)",
+            "ms_per_step": ms, "value": nx * ny / (ms * 1e-3), "unit": UNIT, "steps": 2000, "gpu_launches": int(launches),
+            "finite": bool(torch.isfinite(ens.u).all() and torch.isfinite(ens.p).all()),
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "bytes_per_cell_update": 48,
+                         "note": "one 1.5 MB problem on a 16-CTA thread-block cluster (p resident in shared memory): bound by the "
+                                 "shared-memory bandwidth of 16 SMs and the per-sweep hand-off latency, not by HBM"},
+            "cpu_baseline": {"value": nx * ny * 40 / tc, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": "40 steps in %.2f s (oracle/oracle.c)" % tc}}
+        del ens
+    except Exception as exc:
+        out["direct_fd_cavity256"] = {"error": repr(exc)}
+    # ---- config 3: chorin_spectral, N = 127 (odd N: real spectrum), 1000 steps; the reference scheme overflows within
+    # ~10 steps (SURVEY.md 0.4): inf / NaN do not change fp64 GEMM timing -- timing only
+    try:
+        N = 127
+        D = nns_b200.DirichletBoundaryCondition
+        dxs = 2. / (N - 1.)
+        u_bc = [D(0, 'left', dxs, dxs), D(1, 'right', dxs, dxs), D(0, 'top', dxs, dxs), D(0, 'bottom', dxs, dxs)]
+        v_bc = [D(0, s, dxs, dxs) for s in ('left', 'right', 'top', 'bottom')]
+        flops = 2.0 * 28 * (N - 2) ** 3
+        res = {}
+        for B, steps in ((1, 1000), (1024, 30)):
+            ens = SpectralEnsemble(B, N, N, u_bc=u_bc, v_bc=v_bc, dt=1e-3, rho=1)
+            ens.set_state(*[np.zeros((B, N, N))] * 3)
+            ens.run(9)
+            ms = _events_ms(lambda: ens.run(steps)) / steps
+            tf = flops * B / (ms * 1e-3) / 1e12
+            res[B] = {"members": B, "steps": steps, "ms_per_step": ms, "value": B * N * N / (ms * 1e-3), "unit": UNIT,
+                      "roofline": {"bound": "tensor", "achieved": tf, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                                   "frac": tf / DMMA_PEAK_TFLOPS,
+                                   "note": "fp64 mma.sync m8n8k4 (DMMA) peak measured by scripts/micro/dmma_bench.cu; "
+                                           "28 products of 125^3 per member-step"}}
+            del ens
+        from oracle import spectral as osp
+        S = osp.Setup(N, N, u_bc, v_bc)
+        rng = np.random.default_rng(0)
+        st = [1e-3 * rng.standard_normal((N, N)) for _ in range(5)]
+        t0 = time.perf_counter()
+        nrep = 10
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for _ in range(nrep):
+                ui, vi = osp.predictor(S, 1e-3, st[0], st[1], st[2], st[3])
+                osp.correction(S, 1e-3, 1, ui, vi, st[4])
+        tc = (time.perf_counter() - t0) / nrep
+        out["chorin_spectral127"] = {
+            "config": "chorin_spectral N=127 (Chebyshev collocation, 28 dense 125^3 fp64 products per step), dt=1e-3 (BASELINE configs[2]); "
+                      "values overflow after a few steps as in the reference: timing only",
+            "single": res[1], "ensemble1024": res[1024],
+            "cpu_baseline": {"value": N * N / tc, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                             "sample": "%d steps of oracle/spectral.py (numpy / BLAS threads), %.1f ms per step" % (nrep, tc * 1e3)}}
+    except Exception as exc:
+        out["chorin_spectral127"] = {"error": repr(exc)}
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -265,6 +406,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--members", type=int, default=None, help="override members per GPU")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary configs (extra.configs / extra.slab16384)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -369,6 +511,22 @@ def main():
     except Exception as exc:      # report, never fake
         e2e = {"value": None, "unit": UNIT, "error": str(exc)}
 
+    # ---- BASELINE configs[4] on the same ranks (N >= 2): one 16384^2 grid on row slabs, 5 timed steps (strong scaling)
+    slab_extra = None
+    if world > 1 and not args.no_extras and not args.members:
+        del ens
+        torch.cuda.empty_cache()
+        try:
+            r = slab_measure("slab_cavity16384", 5, 2, rank, world, local, with_clocks=False)
+            if rank == 0:
+                ref_ms = 88.3      # one GPU, profiles/r1_slab16384_n1_bench.json (the N = 1 run does not fit this run's time budget)
+                slab_extra = {"ms_per_step": r["ms_per_step"], "value": r["value"], "unit": UNIT, "scaling": "strong",
+                              "steps": 5, "ticks": r["config"]["ticks_per_step"], "exchange_mode": r["config"]["exchange_mode"],
+                              "efficiency_vs_n1": ref_ms / r["ms_per_step"] / world, "n1_ms_per_step": ref_ms,
+                              "roofline": r["roofline"], "finite": r["config"]["finite"]}
+        except Exception as exc:
+            if rank == 0:
+                slab_extra = {"error": repr(exc)}
     if rank == 0:
         peak, peak_src = peaks()
         kms = float(np.mean(kern_ms))
@@ -395,6 +553,10 @@ def main():
                     out["roofline"]["traffic"] = json.load(f).get(args.workload)
             except Exception:
                 pass
+        if world == 1 and not args.no_extras and not args.members:
+            out["extra"] = {"configs": extra_configs()}
+        if world > 1 and slab_extra is not None:
+            out["extra"] = {"slab16384": slab_extra}
         if world == 1 and not args.no_cpu_baseline:
             val, used, members, el, _ = cpu_port_throughput(nx, ny, nit, dt, budget_s=12.0)
             out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": used, "kind": "port",
