@@ -349,6 +349,33 @@ def extra_configs():
         del ens
     except Exception as exc:
         out["direct_fd_cavity256"] = {"error": repr(exc)}
+    # ---- config 2b: the same grid as a channel, periodic in the differenced axis 1 with a body force (an extension: the
+    # reference has neither; reference-unpinned, oracle = numpy restatement with wrapped indices)
+    try:
+        nx = ny = 256
+        D, Nm = nns_b200.DirichletBoundaryCondition, nns_b200.NeumannBoundaryCondition
+        dx = dy = 2. / (nx - 1)
+        walls = lambda cls: [cls(0.0, 'left', dx, dy), cls(0.0, 'right', dx, dy)]     # noqa: E731
+        ens = DirectEnsemble(1, nx, ny, u_bc=walls(D), v_bc=walls(D), p_bc=walls(Nm), nit=50, dt=1e-4, rho=1, nu=0.1,
+                             periodic_x=True, force_x=1.0)
+        ens.run(20)
+        ms = _events_ms(lambda: ens.run(2000)) / 2000
+        z = np.zeros((nx, ny))
+        t0 = time.perf_counter()
+        ofd.direct_periodic_simulate(z, z, z, walls(D), walls(D), walls(Nm), 3, 50, 1e-4, 1.0, 0.1, 1.0)
+        tc = (time.perf_counter() - t0) / 3
+        ach = 48 * nx * ny / (ms * 1e-3) / 1e9
+        out["direct_fd_channel256_periodic"] = {
+            "config": "direct_fd channel 256x256, periodic x-BC + body force, nt=2000, nit=50, dt=1e-4 (BASELINE configs[1] as named; "
+                      "extension, reference-unpinned)",
+            "ms_per_step": ms, "value": nx * ny / (ms * 1e-3), "unit": UNIT, "steps": 2000,
+            "finite": bool(torch.isfinite(ens.u).all() and torch.isfinite(ens.p).all()), "u_mean": float(ens.u.mean()),
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "bytes_per_cell_update": 48},
+            "cpu_baseline": {"value": nx * ny / tc, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": "3 steps of the numpy restatement (oracle/fd.py direct_periodic_simulate), %.0f ms per step" % (tc * 1e3)}}
+        del ens
+    except Exception as exc:
+        out["direct_fd_channel256_periodic"] = {"error": repr(exc)}
     # ---- config 3: chorin_spectral, N = 127 (odd N: real spectrum), 1000 steps; the reference scheme overflows within
     # ~10 steps: inf / NaN do not change fp64 GEMM timing -- timing only
     try:

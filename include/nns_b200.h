@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NNS_ABI_VERSION 1
+#define NNS_ABI_VERSION 2
 #define NNS_MAX_BC 8 /* per field */
 
 typedef enum nns_status {
@@ -69,9 +69,15 @@ typedef struct nns_params {
     double tol;     /* SOR exit tolerance; <= 0 selects the reference's 5e-6 (chorin_fd:183) */
     int32_t device; /* CUDA ordinal, -1 = current device */
     int32_t flags;  /* NNS_FLAG_* */
+    double force_x; /* direct_fd with NNS_FLAG_PERIODIC_X: constant source added to u (dt * force_x per step), else ignored */
 } nns_params;
 
 #define NNS_FLAG_CHECK_FINITE 1 /* count non-finite outputs; *_host calls then return NNS_ERR_NONFINITE */
+/* direct_fd only, EXTENSION (not in the reference, which has Dirichlet / Neumann conditions only, src/boundary.py:29-86;
+ * BASELINE.json config 2 asks for it): the differenced axis 1 (dx, columns) is periodic -- every column is an interior
+ * column whose neighbours wrap around -- and force_x drives the flow; the BC lists may then only name the sides
+ * 'left' / 'right' (rows 0 and nx-1: the channel walls). */
+#define NNS_FLAG_PERIODIC_X 4
 
 typedef struct nns_handle nns_handle;
 

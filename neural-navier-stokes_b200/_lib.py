@@ -11,6 +11,7 @@ SOLVER_CHORIN_FD, SOLVER_DIRECT_FD, SOLVER_CHORIN_SPECTRAL = 0, 1, 2
 METHODS = {"explicit": 0, "semi_implicit": 1}
 FIELD_U, FIELD_V, FIELD_P = 0, 1, 2
 FLAG_CHECK_FINITE = 1
+FLAG_PERIODIC_X = 4
 SPECTRAL_N_OPERATORS = 29
 MAX_BC = 8
 
@@ -24,7 +25,7 @@ class NnsParams(C.Structure):
     _fields_ = [("solver", C.c_int32), ("method", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32),
                 ("batch", C.c_int32), ("nit", C.c_int32), ("dt", C.c_double), ("rho", C.c_double),
                 ("nu", C.c_double), ("beta", C.c_double), ("tol", C.c_double), ("device", C.c_int32),
-                ("flags", C.c_int32)]
+                ("flags", C.c_int32), ("force_x", C.c_double)]
 
 
 class NnsError(RuntimeError):
@@ -116,13 +117,14 @@ class Handle:
 
     def __init__(self, solver, nx, ny, nit, dt, rho, nu, beta=1.25, method="explicit", batch=1,
                  u_bc=(), v_bc=(), p_bc=(), nu_per_member=None, bc_value_per_member=None, tol=0.0,
-                 device=-1, check_finite=True):
+                 device=-1, check_finite=True, periodic_x=False, force_x=0.0):
         L = lib()
         if method not in METHODS:
             raise Exception("method not recognized: {}".format(method))
         self.params = NnsParams(solver, METHODS[method], nx, ny, batch, nit, float(dt), float(rho),
                                 float(nu), float(beta), float(tol), device,
-                                FLAG_CHECK_FINITE if check_finite else 0)
+                                (FLAG_CHECK_FINITE if check_finite else 0) | (FLAG_PERIODIC_X if periodic_x else 0),
+                                float(force_x))
         arr, n = bc_table(u_bc, v_bc, p_bc)
         self.n_bcs = n
         # the kernels apply Neumann conditions with the solver's spacing; the reference uses the BC object's own

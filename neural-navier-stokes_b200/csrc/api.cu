@@ -211,6 +211,15 @@ static int32_t create_impl(const nns_params *P, const nns_bc *bcs, int32_t n_bcs
         L.side[L.n] = b.side; L.type[L.n] = b.type; L.value[L.n] = b.value; L.slot[L.n] = k;
         L.n++;
     }
+    if (P->flags & NNS_FLAG_PERIODIC_X) {
+        if (P->solver != NNS_SOLVER_DIRECT_FD) { set_error("NNS_FLAG_PERIODIC_X is a direct_fd extension"); return NNS_ERR_INVALID; }
+        for (int f = 0; f < 3; ++f)
+            for (int k = 0; k < h->bc[f].n; ++k)
+                if (h->bc[f].side[k] == NNS_SIDE_BOTTOM || h->bc[f].side[k] == NNS_SIDE_TOP) {
+                    set_error("periodic x: boundary conditions may only name 'left' / 'right' (the channel walls)");
+                    return NNS_ERR_INVALID;
+                }
+    }
     if (nu_b) {
         NNS_CUDA(cudaMalloc(&h->d_nu, sizeof(double) * g.batch));
         NNS_CUDA(cudaMemcpy(h->d_nu, nu_b, sizeof(double) * g.batch, cudaMemcpyHostToDevice));

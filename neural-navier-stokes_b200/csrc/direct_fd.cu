@@ -31,6 +31,7 @@ struct DirectArgs {
     int n_bcs;
     int nsteps, nsteps_total, step0;
     int flags;
+    double force_x;             // periodic-x extension: source of u
     double *u, *v, *p;          // [batch][nx][ny], advanced in place
     double *su, *sv;            // scratch (ping-pong partner of u, v)
     double *traj_u, *traj_v, *traj_p;
@@ -75,6 +76,9 @@ __global__ void __launch_bounds__(1024, 1) direct_chip_kernel(const DirectArgs a
     const double r2dx = 1.0 / (2.0 * dx), r2dy = 1.0 / (2.0 * dy), rdt = 1.0 / dt;
     double *ug = a.u + (size_t)b * N, *vg = a.v + (size_t)b * N, *pg = a.p + (size_t)b * N;
     double *us = a.su + (size_t)b * N, *vs = a.sv + (size_t)b * N;
+    // periodic-x extension: every column is interior, the column neighbours wrap around
+    const bool per = a.flags & NNS_FLAG_PERIODIC_X;
+    const double fdt = per ? a.force_x * dt : 0.0;
 
     for (int i = warp; i < nx; i += nwarps)
         for (int j = lane; j < ny; j += 32) P0[i * pitch + j] = pg[(size_t)i * ny + j];
@@ -87,10 +91,11 @@ __global__ void __launch_bounds__(1024, 1) direct_chip_kernel(const DirectArgs a
         for (int i = warp; i < nx; i += nwarps)
             for (int j = lane; j < ny; j += 32) {
                 double bb = 0.0;
-                if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1) {
-                    const size_t q = (size_t)i * ny + j;
-                    const double ux = (uo[q + 1] - uo[q - 1]) * r2dx, vy = (vo[q + ny] - vo[q - ny]) * r2dy;
-                    const double uy = (uo[q + ny] - uo[q - ny]) * r2dy, vx = (vo[q + 1] - vo[q - 1]) * r2dx;
+                if (i > 0 && i < nx - 1 && (per || (j > 0 && j < ny - 1))) {
+                    const size_t q = (size_t)i * ny + j, rq = (size_t)i * ny;
+                    const int jp = j < ny - 1 ? j + 1 : 0, jm = j > 0 ? j - 1 : ny - 1;
+                    const double ux = (uo[rq + jp] - uo[rq + jm]) * r2dx, vy = (vo[q + ny] - vo[q - ny]) * r2dy;
+                    const double uy = (uo[q + ny] - uo[q - ny]) * r2dy, vx = (vo[rq + jp] - vo[rq + jm]) * r2dx;
                     bb = rho * (rdt * (ux + vy)) - ux * ux - 2.0 * (uy * vx) - vy * vy;
                 }
                 Bs[i * pitch + j] = kb * bb;
@@ -103,8 +108,10 @@ __global__ void __launch_bounds__(1024, 1) direct_chip_kernel(const DirectArgs a
                 for (int j = lane; j < ny; j += 32) {
                     const int q = i * pitch + j;
                     double r = Pc[q];
-                    if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1)
-                        r = (Pc[q + 1] + Pc[q - 1]) * cx + (Pc[q + pitch] + Pc[q - pitch]) * cy - Bs[q];
+                    if (i > 0 && i < nx - 1 && (per || (j > 0 && j < ny - 1))) {
+                        const int jp = j < ny - 1 ? j + 1 : 0, jm = j > 0 ? j - 1 : ny - 1;
+                        r = (Pc[i * pitch + jp] + Pc[i * pitch + jm]) * cx + (Pc[q + pitch] + Pc[q - pitch]) * cy - Bs[q];
+                    }
                     Pn[q] = r;
                 }
             __syncthreads();
@@ -119,12 +126,14 @@ __global__ void __launch_bounds__(1024, 1) direct_chip_kernel(const DirectArgs a
                 const size_t q = (size_t)i * ny + j;
                 const double uc = uo[q], vc = vo[q];
                 double ru = uc, rv = vc;
-                if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1) {
+                if (i > 0 && i < nx - 1 && (per || (j > 0 && j < ny - 1))) {
                     const int s = i * pitch + j;
-                    const double uW = uo[q - 1], uE = uo[q + 1], uN = uo[q - ny], uS = uo[q + ny];
-                    const double vW = vo[q - 1], vE = vo[q + 1], vN = vo[q - ny], vS = vo[q + ny];
-                    ru = uc - uc * ax * (uc - uW) - vc * ay * (uc - uN) - kpx * (Pc[s + 1] - Pc[s - 1]) +
-                         nu * (kdx * (uE - 2.0 * uc + uW) + kdy * (uS - 2.0 * uc + uN));
+                    const int jp = j < ny - 1 ? j + 1 : 0, jm = j > 0 ? j - 1 : ny - 1;
+                    const size_t rq = (size_t)i * ny;
+                    const double uW = uo[rq + jm], uE = uo[rq + jp], uN = uo[q - ny], uS = uo[q + ny];
+                    const double vW = vo[rq + jm], vE = vo[rq + jp], vN = vo[q - ny], vS = vo[q + ny];
+                    ru = uc - uc * ax * (uc - uW) - vc * ay * (uc - uN) - kpx * (Pc[i * pitch + jp] - Pc[i * pitch + jm]) +
+                         nu * (kdx * (uE - 2.0 * uc + uW) + kdy * (uS - 2.0 * uc + uN)) + fdt;
                     rv = vc - uc * ax * (vc - vW) - vc * ay * (vc - vN) - kpy * (Pc[s + pitch] - Pc[s - pitch]) +
                          nu * (kdx * (vE - 2.0 * vc + vW) + kdy * (vS - 2.0 * vc + vN));
                 }
@@ -246,6 +255,8 @@ __global__ void __launch_bounds__(1024, 1) direct_cluster_kernel(const DirectArg
     const double r2dx = 1.0 / (2.0 * dx), r2dy = 1.0 / (2.0 * dy), rdt = 1.0 / dt;
     double *ug = a.u + (size_t)b * N, *vg = a.v + (size_t)b * N, *pg = a.p + (size_t)b * N;
     double *us = a.su + (size_t)b * N, *vs = a.sv + (size_t)b * N;
+    const bool per = a.flags & NNS_FLAG_PERIODIC_X;          // periodic-x extension: the column neighbours wrap around
+    const double fdt = per ? a.force_x * dt : 0.0;
 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dsm_u32(&hbar[0])));
@@ -270,10 +281,11 @@ __global__ void __launch_bounds__(1024, 1) direct_cluster_kernel(const DirectArg
             const int i = i0 + li - 1;
             for (int j = lane; j < ny; j += 32) {
                 double bb = 0.0;
-                if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1) {
-                    const size_t q = (size_t)i * ny + j;
-                    const double ux = (uo[q + 1] - uo[q - 1]) * r2dx, vy = (vo[q + ny] - vo[q - ny]) * r2dy;
-                    const double uy = (uo[q + ny] - uo[q - ny]) * r2dy, vx = (vo[q + 1] - vo[q - 1]) * r2dx;
+                if (i > 0 && i < nx - 1 && (per || (j > 0 && j < ny - 1))) {
+                    const size_t q = (size_t)i * ny + j, rq = (size_t)i * ny;
+                    const int jp = j < ny - 1 ? j + 1 : 0, jm = j > 0 ? j - 1 : ny - 1;
+                    const double ux = (uo[rq + jp] - uo[rq + jm]) * r2dx, vy = (vo[q + ny] - vo[q - ny]) * r2dy;
+                    const double uy = (uo[q + ny] - uo[q - ny]) * r2dy, vx = (vo[rq + jp] - vo[rq + jm]) * r2dx;
                     bb = rho * (rdt * (ux + vy)) - ux * ux - 2.0 * (uy * vx) - vy * vy;
                 }
                 Bs[li * pitch + j] = kb * bb;
@@ -287,8 +299,10 @@ __global__ void __launch_bounds__(1024, 1) direct_cluster_kernel(const DirectArg
                 for (int j = lane; j < ny; j += 32) {
                     const int q = li * pitch + j;
                     double rr = Pc[q];
-                    if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1)
-                        rr = (Pc[q + 1] + Pc[q - 1]) * cx + (Pc[q + pitch] + Pc[q - pitch]) * cy - Bs[q];
+                    if (i > 0 && i < nx - 1 && (per || (j > 0 && j < ny - 1))) {
+                        const int jp = j < ny - 1 ? j + 1 : 0, jm = j > 0 ? j - 1 : ny - 1;
+                        rr = (Pc[li * pitch + jp] + Pc[li * pitch + jm]) * cx + (Pc[q + pitch] + Pc[q - pitch]) * cy - Bs[q];
+                    }
                     Pn[q] = rr;
                 }
             }
@@ -327,12 +341,14 @@ __global__ void __launch_bounds__(1024, 1) direct_cluster_kernel(const DirectArg
                 const size_t q = (size_t)i * ny + j;
                 const double uc = uo[q], vc = vo[q];
                 double ru = uc, rv = vc;
-                if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1) {
+                if (i > 0 && i < nx - 1 && (per || (j > 0 && j < ny - 1))) {
                     const int sq = li * pitch + j;
-                    const double uW = uo[q - 1], uE = uo[q + 1], uN = uo[q - ny], uS = uo[q + ny];
-                    const double vW = vo[q - 1], vE = vo[q + 1], vN = vo[q - ny], vS = vo[q + ny];
-                    ru = uc - uc * ax * (uc - uW) - vc * ay * (uc - uN) - kpx * (Pc[sq + 1] - Pc[sq - 1]) +
-                         nu * (kdx * (uE - 2.0 * uc + uW) + kdy * (uS - 2.0 * uc + uN));
+                    const int jp = j < ny - 1 ? j + 1 : 0, jm = j > 0 ? j - 1 : ny - 1;
+                    const size_t rq = (size_t)i * ny;
+                    const double uW = uo[rq + jm], uE = uo[rq + jp], uN = uo[q - ny], uS = uo[q + ny];
+                    const double vW = vo[rq + jm], vE = vo[rq + jp], vN = vo[q - ny], vS = vo[q + ny];
+                    ru = uc - uc * ax * (uc - uW) - vc * ay * (uc - uN) - kpx * (Pc[li * pitch + jp] - Pc[li * pitch + jm]) +
+                         nu * (kdx * (uE - 2.0 * uc + uW) + kdy * (uS - 2.0 * uc + uN)) + fdt;
                     rv = vc - uc * ax * (vc - vW) - vc * ay * (vc - vN) - kpy * (Pc[sq + pitch] - Pc[sq - pitch]) +
                          nu * (kdx * (vE - 2.0 * vc + vW) + kdy * (vS - 2.0 * vc + vN));
                 }
@@ -478,7 +494,7 @@ int direct_run(nns_handle *h, double *u, double *v, double *p, int nsteps, doubl
         DirectArgs a{};
         a.g = g; a.ubc = h->bc[0]; a.vbc = h->bc[1]; a.pbc = h->bc[2];
         a.nu_b = h->d_nu; a.bcval = h->d_bcval; a.n_bcs = h->n_bcs;
-        a.nsteps = nsteps; a.nsteps_total = nsteps; a.step0 = 0; a.flags = h->params.flags;
+        a.nsteps = nsteps; a.nsteps_total = nsteps; a.step0 = 0; a.flags = h->params.flags; a.force_x = h->params.force_x;
         a.u = u; a.v = v; a.p = p; a.su = h->d_scratch[0]; a.sv = h->d_scratch[1];
         a.traj_u = tu; a.traj_v = tv; a.traj_p = tp; a.nonfinite = h->d_nonfinite;
         const long cells = (long)g.nx * g.ny;
@@ -501,7 +517,7 @@ int direct_run(nns_handle *h, double *u, double *v, double *p, int nsteps, doubl
             DirectArgs a{};
             a.g = g; a.ubc = h->bc[0]; a.vbc = h->bc[1]; a.pbc = h->bc[2];
             a.nu_b = h->d_nu; a.bcval = h->d_bcval; a.n_bcs = h->n_bcs;
-            a.nsteps = nsteps; a.nsteps_total = nsteps; a.step0 = 0; a.flags = h->params.flags;
+            a.nsteps = nsteps; a.nsteps_total = nsteps; a.step0 = 0; a.flags = h->params.flags; a.force_x = h->params.force_x;
             a.u = u; a.v = v; a.p = p; a.su = h->d_scratch[0]; a.sv = h->d_scratch[1];
             a.traj_u = tu; a.traj_v = tv; a.traj_p = tp; a.nonfinite = h->d_nonfinite;
             NNS_CUDA(cudaFuncSetAttribute(direct_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
@@ -528,6 +544,10 @@ int direct_run(nns_handle *h, double *u, double *v, double *p, int nsteps, doubl
         }
     }
     // stream path
+    if (h->params.flags & NNS_FLAG_PERIODIC_X) {
+        set_error("direct_fd periodic-x extension: the grid must fit the chip or the cluster path (nx * ny * 24 B over at most 16 SMs)");
+        return NNS_ERR_UNSUPPORTED;
+    }
     if ((rc = ensure(&h->d_b, bytes)) || (rc = ensure(&h->d_p2, bytes))) return rc;
     const dim3 blk(128), grd((g.ny + 127) / 128, g.nx, g.batch);
     double *uc = u, *vc = v, *un = h->d_scratch[0], *vn = h->d_scratch[1];

@@ -16,7 +16,10 @@ from .. import _lib
 
 class NavierStokesSystem():
     def __init__(self, u_ic, v_ic, p_ic, u_bc, v_bc, p_bc,
-                 nt=200, nit=50, nx=50, ny=50, dt=0.001, rho=1, nu=0.1):
+                 nt=200, nit=50, nx=50, ny=50, dt=0.001, rho=1, nu=0.1, periodic_x=False, force_x=0.0):
+        # periodic_x / force_x: EXTENSION (channel flow of BASELINE.json config 2; the reference has neither): axis 1
+        # is periodic and force_x * dt is added to u every step; the BC lists then only name 'left' / 'right'
+        self.periodic_x, self.force_x = bool(periodic_x), float(force_x)
         self.u_ic, self.v_ic, self.p_ic = u_ic, v_ic, p_ic
         self.u_bc, self.v_bc, self.p_bc = u_bc, v_bc, p_bc
         self.nt, self.dt, self.nx, self.ny = nt, dt, nx, ny
@@ -26,7 +29,7 @@ class NavierStokesSystem():
 
     def _key(self):
         bcs = tuple((bc.type, bc.boundary, float(bc.value)) for lst in (self.u_bc, self.v_bc, self.p_bc) for bc in lst)
-        return (self.nx, self.ny, self.nit, self.dt, self.rho, self.nu, bcs)
+        return (self.nx, self.ny, self.nit, self.dt, self.rho, self.nu, bcs, self.periodic_x, self.force_x)
 
     def _h(self):
         # the reference reads its attributes at every step: rebuild the device handle when they have changed
@@ -36,7 +39,8 @@ class NavierStokesSystem():
         if self._handle is None:
             self._handle_key = self._key()
             self._handle = _lib.Handle(_lib.SOLVER_DIRECT_FD, self.nx, self.ny, self.nit, self.dt, self.rho,
-                                       self.nu, batch=1, u_bc=self.u_bc, v_bc=self.v_bc, p_bc=self.p_bc)
+                                       self.nu, batch=1, u_bc=self.u_bc, v_bc=self.v_bc, p_bc=self.p_bc,
+                                       periodic_x=self.periodic_x, force_x=self.force_x)
         return self._handle
 
     def _work(self, a, name):

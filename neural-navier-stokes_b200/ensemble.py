@@ -24,7 +24,8 @@ class _Ensemble:
     solver = None
 
     def __init__(self, batch, nx, ny, *, u_bc, v_bc, p_bc, nit=50, dt=0.001, rho=1, nu=0.1, beta=1.25,
-                 method='explicit', bc_values=None, device=None, check_finite=False, tol=0.0):
+                 method='explicit', bc_values=None, device=None, check_finite=False, tol=0.0, periodic_x=False,
+                 force_x=0.0):
         if not torch.cuda.is_available():
             raise RuntimeError("nns_b200 ensembles need a CUDA device (no CPU fallback)")
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
@@ -34,7 +35,8 @@ class _Ensemble:
             self.handle = _lib.Handle(self.solver, nx, ny, nit, dt, rho, float(np.ravel(nu)[0]), beta=beta,
                                       method=method, batch=self.batch, u_bc=u_bc, v_bc=v_bc, p_bc=p_bc,
                                       nu_per_member=nu_arr, bc_value_per_member=bc_values, tol=tol,
-                                      device=self.device.index, check_finite=check_finite)
+                                      device=self.device.index, check_finite=check_finite, periodic_x=periodic_x,
+                                      force_x=force_x)
         self._L = _lib.lib()
 
     def _zeros(self):

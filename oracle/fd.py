@@ -225,3 +225,55 @@ def set_threads(n=None):
     n = int(n or host_cores())
     lib().orc_set_threads(n)
     return n
+
+
+def direct_periodic_simulate(u0, v0, p0, u_bc, v_bc, p_bc, nt, nit, dt, rho, nu, force_x):
+    """EXTENSION oracle (reference-unpinned: the reference has no periodic condition and no body force; BASELINE.json
+    config 2 asks for a periodic-x channel): src/direct_fd/simulate.py:56-127 restated with numpy, where every column
+    slice [1:-1] / [2:] / [0:-2] of the differenced axis 1 becomes the full axis / np.roll(-1) / np.roll(+1) and the
+    u equation gains + force_x * dt (Barba's channel flow, step 12 of the "12 steps", in the reference's own operation
+    order).  BC entries: (side, type, value) with side in ('left', 'right') only.  Returns (u, v, p) trajectories."""
+    nx, ny = u0.shape
+    dx, dy = 2. / (nx - 1), 2. / (ny - 1)
+    u, v, p = (np.array(a, dtype=np.float64) for a in (u0, v0, p0))
+
+    def apply(A, bcs):
+        for bc in bcs:
+            side, typ, val = (bc.boundary, bc.type, float(bc.value)) if hasattr(bc, "boundary") else bc
+            assert side in ("left", "right"), "periodic x: only the walls (rows 0 and nx-1) carry conditions"
+            if typ == "dirichlet":
+                A[0 if side == "left" else -1, :] = val
+            elif side == "left":
+                A[0, :] = A[1, :] - dx * val
+            else:
+                A[-1, :] = A[-2, :] + dx * val
+        return A
+
+    E = lambda a: np.roll(a, -1, axis=1)      # noqa: E731  column j + 1
+    W = lambda a: np.roll(a, 1, axis=1)       # noqa: E731  column j - 1
+    tu, tv, tp = [], [], []
+    for _ in range(nt):
+        un, vn = u.copy(), v.copy()
+        b = np.zeros_like(u)
+        b[1:-1, :] = (rho * (1 / dt * ((E(u)[1:-1] - W(u)[1:-1]) / (2 * dx) + (v[2:, :] - v[0:-2, :]) / (2 * dy))) -
+                      ((E(u)[1:-1] - W(u)[1:-1]) / (2 * dx))**2 -
+                      2 * ((u[2:, :] - u[0:-2, :]) / (2 * dy) * (E(v)[1:-1] - W(v)[1:-1]) / (2 * dx)) -
+                      ((v[2:, :] - v[0:-2, :]) / (2 * dy))**2)
+        for _q in range(nit):
+            pn = p.copy()
+            p[1:-1, :] = (((E(pn)[1:-1] + W(pn)[1:-1]) * dy**2 + (pn[2:, :] + pn[0:-2, :]) * dx**2) /
+                          (2 * (dx**2 + dy**2)) - dx**2 * dy**2 / (2 * (dx**2 + dy**2)) * b[1:-1, :])
+            p = apply(p, p_bc)
+        u[1:-1, :] = (un[1:-1] - un[1:-1] * dt / dx * (un[1:-1] - W(un)[1:-1]) -
+                      vn[1:-1] * dt / dy * (un[1:-1] - un[0:-2]) -
+                      dt / (2 * rho * dx) * (E(p)[1:-1] - W(p)[1:-1]) +
+                      nu * (dt / dx**2 * (E(un)[1:-1] - 2 * un[1:-1] + W(un)[1:-1]) +
+                            dt / dy**2 * (un[2:] - 2 * un[1:-1] + un[0:-2])) + force_x * dt)
+        v[1:-1, :] = (vn[1:-1] - un[1:-1] * dt / dx * (vn[1:-1] - W(vn)[1:-1]) -
+                      vn[1:-1] * dt / dy * (vn[1:-1] - vn[0:-2]) -
+                      dt / (2 * rho * dy) * (p[2:] - p[0:-2]) +
+                      nu * (dt / dx**2 * (E(vn)[1:-1] - 2 * vn[1:-1] + W(vn)[1:-1]) +
+                            dt / dy**2 * (vn[2:] - 2 * vn[1:-1] + vn[0:-2])))
+        u, v = apply(u, u_bc), apply(v, v_bc)
+        tu.append(u.copy()); tv.append(v.copy()); tp.append(p.copy())
+    return np.stack(tu), np.stack(tv), np.stack(tp)

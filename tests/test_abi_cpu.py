@@ -28,12 +28,12 @@ def test_library_is_built_and_exports_header_symbols():
     for name in decl:
         assert hasattr(L, name), "missing export " + name
     assert sorted(_lib.exported_symbols()) == decl       # the ctypes prototypes cover the whole header
-    assert _lib.lib().nns_abi_version() == 1
+    assert _lib.lib().nns_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.NnsBC) == 24
-    assert ctypes.sizeof(_lib.NnsParams) == 6 * 4 + 5 * 8 + 2 * 4
+    assert ctypes.sizeof(_lib.NnsParams) == 6 * 4 + 5 * 8 + 2 * 4 + 8      # + force_x (ABI version 2)
 
 
 @pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")

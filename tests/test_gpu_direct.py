@@ -98,3 +98,42 @@ def test_direct_chip_cluster_and_stream_paths_agree(oracle_fd, monkeypatch, shap
         for other in ("cluster", "stream"):
             d = float((out["chip"][k] - out[other][k]).norm() / out["chip"][k].norm())
             assert d <= 1e-13, (k, other, d)
+
+
+@pytest.mark.parametrize("shape,mode", [((41, 48), "chip"), ((96, 128), "cluster"), ((256, 256), "cluster")])
+def test_direct_periodic_channel_extension(oracle_fd, monkeypatch, shape, mode):
+    """BASELINE config 2b: channel flow, periodic in the differenced axis 1 with a body force (an EXTENSION: the reference
+    has neither; reference-unpinned).  Oracle = numpy restatement of direct_fd:56-127 with wrapped column indices
+    (oracle/fd.py direct_periodic_simulate); walls u = v = 0, dp/dn = 0; smooth start; chip and cluster paths."""
+    import torch
+    import nns_b200
+    from nns_b200.ensemble import DirectEnsemble
+    D, Nm = nns_b200.DirichletBoundaryCondition, nns_b200.NeumannBoundaryCondition
+    nx, ny = shape
+    dx, dy = 2. / (nx - 1), 2. / (ny - 1)
+    walls = lambda cls, val: [cls(val, 'left', dx, dy), cls(val, 'right', dx, dy)]      # noqa: E731
+    u_bc, v_bc, p_bc = walls(D, 0.0), walls(D, 0.0), walls(Nm, 0.0)
+    x = np.linspace(0, 2 * np.pi, ny, endpoint=False)[None, :]
+    y = np.linspace(-1, 1, nx)[:, None]
+    u0 = 0.3 * (1 - y ** 2) * (1 + 0.2 * np.sin(2 * x))
+    v0 = 0.05 * (1 - y ** 2) * np.cos(x)
+    p0 = 0.1 * np.cos(3 * x) * y
+    nt, nit, dt = (6, 11, 2e-4) if nx < 200 else (3, 50, 1e-4)
+    monkeypatch.setenv("NNS_DIRECT_MODE", mode)
+    ens = DirectEnsemble(1, nx, ny, u_bc=u_bc, v_bc=v_bc, p_bc=p_bc, nit=nit, dt=dt, rho=1.0, nu=0.1, periodic_x=True, force_x=1.0)
+    ens.set_state(u0[None], v0[None], p0[None])
+    for f in (0, 1, 2):
+        ens.apply_bc(f, (ens.u, ens.v, ens.p)[f])
+    tu, tv, tp = ens.run(nt, trajectory=True)
+    torch.cuda.synchronize()
+    monkeypatch.delenv("NNS_DIRECT_MODE")
+    assert ens.launches <= 4
+    a0 = [u0.copy(), v0.copy(), p0.copy()]
+    for A, val in ((a0[0], 0.0), (a0[1], 0.0)):
+        A[0, :] = val; A[-1, :] = val
+    a0[2][0, :] = a0[2][1, :]; a0[2][-1, :] = a0[2][-2, :]
+    ou, ov, op = oracle_fd.direct_periodic_simulate(a0[0], a0[1], a0[2], u_bc, v_bc, p_bc, nt, nit, dt, 1.0, 0.1, 1.0)
+    for n in range(nt):
+        assert rel_l2(tu[0, n].cpu().numpy(), ou[n]) <= TOL and rel_l2(tv[0, n].cpu().numpy(), ov[n]) <= TOL, n
+        assert rel_l2(tp[0, n].cpu().numpy(), op[n]) <= TOL, n
+    assert abs(float(tu[0, -1, 1:-1].mean()) - float(ou[-1][1:-1].mean())) < 1e-12      # the body force really drives u
