@@ -1,5 +1,6 @@
 // api.cu -- extern "C" entry points of libnns_b200 (see include/nns_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <math.h>
 
 #include <new>
@@ -223,10 +224,16 @@ static int32_t create_impl(const nns_params *P, const nns_bc *bcs, int32_t n_bcs
     if (nu_b) {
         NNS_CUDA(cudaMalloc(&h->d_nu, sizeof(double) * g.batch));
         NNS_CUDA(cudaMemcpy(h->d_nu, nu_b, sizeof(double) * g.batch, cudaMemcpyHostToDevice));
+        h->h_nu = static_cast<double *>(malloc(sizeof(double) * g.batch));
+        if (!h->h_nu) { set_error("out of host memory"); return NNS_ERR_NOMEM; }
+        memcpy(h->h_nu, nu_b, sizeof(double) * g.batch);
     }
     if (bcval_b && n_bcs > 0) {
         NNS_CUDA(cudaMalloc(&h->d_bcval, sizeof(double) * (size_t)g.batch * n_bcs));
         NNS_CUDA(cudaMemcpy(h->d_bcval, bcval_b, sizeof(double) * (size_t)g.batch * n_bcs, cudaMemcpyHostToDevice));
+        h->h_bcval = static_cast<double *>(malloc(sizeof(double) * (size_t)g.batch * n_bcs));
+        if (!h->h_bcval) { set_error("out of host memory"); return NNS_ERR_NOMEM; }
+        memcpy(h->h_bcval, bcval_b, sizeof(double) * (size_t)g.batch * n_bcs);
     }
     NNS_CUDA(cudaMalloc(&h->d_nonfinite, sizeof(unsigned long long)));
     NNS_CUDA(cudaMemset(h->d_nonfinite, 0, sizeof(unsigned long long)));
@@ -249,6 +256,7 @@ int32_t nns_destroy(nns_handle *h) {
     for (int k = 0; k < 4; ++k) cudaFree(h->d_scratch[k]);
     for (int k = 0; k < 7; ++k) cudaFree(h->d_stage[k]);
     for (int k = 0; k < 10; ++k) cudaFree(h->d_pool[k]);
+    free(h->h_nu); free(h->h_bcval);
     for (int k = 0; k < 4; ++k) if (h->streams[k]) cudaStreamDestroy(h->streams[k]);
     delete h;
     return NNS_OK;

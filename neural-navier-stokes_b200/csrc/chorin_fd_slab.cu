@@ -88,6 +88,7 @@ struct SlabState {
     int I0 = 0, I1 = 0;           // owned tile rows
     NcclComm comm = nullptr;
     double *d_cprime = nullptr, *d_p0 = nullptr;    // [nrows + 2][ny]
+    double *d_thomas = nullptr;                     // semi-implicit: elimination coefficients of the two ADI stages, 2 x 2 nx
     double *d_own[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // single-GPU run(): haloed copies
     int *d_flags = nullptr;       // [64] per-sweep "not converged" flags
     int *h_flags = nullptr;       // pinned
@@ -152,6 +153,85 @@ __global__ void slab_predictor_kernel(SlabGeom g, const double *__restrict__ uc,
     }
     un[q] = ru;
     vn[q] = rv;
+}
+
+// ---- semi-implicit predictor on a whole grid in HBM (single GPU; chorin_fd:93-167): AB2 advection + Crank-Nicolson ADI,
+// all four solves along axis 0 with the matrices of :105-121 (diagonal (2/nu) dx^2 + 2 dt, the reference's precedence),
+// the same arithmetic as phase_predictor of chorin_fd_chip.cu.  Columns are independent: one thread per interior
+// column marches down the rows (coalesced across the columns), the elimination coefficients are shared by all columns.
+__global__ void semi_rhs_kernel(SlabGeom g, const double *__restrict__ uc, const double *__restrict__ vc,
+                                const double *__restrict__ up, const double *__restrict__ vp,
+                                double *__restrict__ un, double *__restrict__ vn) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = g.row0 + blockIdx.y;
+    if (j >= g.ny || i >= g.row1) return;
+    const size_t q = g.v.at(i, j);
+    const int ny = g.ny;
+    const double u0 = uc[q], v0 = vc[q];
+    double ru = u0, rv = v0;
+    if (i > 0 && i < g.nx - 1 && j > 0 && j < ny - 1) {
+        const double dt = g.dt, nu = g.nu, dx2 = g.dx * g.dx, dy2 = g.dy * g.dy;
+        const double r2dx = 1.0 / (2.0 * g.dx), r2dy = 1.0 / (2.0 * g.dy), rdx2 = 1.0 / dx2, rdy2 = 1.0 / dy2;
+        const double kx = 2.0 / nu * dx2;
+        const double u1c = up[q], v1c = vp[q];
+        const double uS = uc[q + ny], uN = uc[q - ny], uE = uc[q + 1], uW = uc[q - 1];
+        const double vS = vc[q + ny], vN = vc[q - ny], vE = vc[q + 1], vW = vc[q - 1];
+        const double pS = up[q + ny], pN = up[q - ny], pE = up[q + 1], pW = up[q - 1];
+        const double qS = vp[q + ny], qN = vp[q - ny], qE = vp[q + 1], qW = vp[q - 1];
+        const double uHn = u0 * (uS - uN) * r2dx + v0 * (uE - uW) * r2dy;
+        const double uHn1 = u1c * (pS - pN) * r2dx + v1c * (pE - pW) * r2dy;
+        const double vHn = u0 * (vS - vN) * r2dx + v0 * (vE - vW) * r2dy;
+        const double vHn1 = u1c * (qS - qN) * r2dx + v1c * (qE - qW) * r2dy;
+        const double uC2 = dt * nu * ((uS - 2.0 * u0 + uN) * rdx2 + (uE - 2.0 * u0 + uW) * rdy2);
+        const double vC2 = dt * nu * ((vS - 2.0 * v0 + vN) * rdx2 + (vE - 2.0 * v0 + vW) * rdy2);
+        ru = kx * (0.5 * dt * (3.0 * uHn - uHn1) + uC2);
+        rv = kx * (0.5 * dt * (3.0 * vHn - vHn1) + vC2);
+    }
+    un[q] = ru;
+    vn[q] = rv;
+}
+
+// cpr[i] = c'_i, cpr[nx + i] = 1 / m_i of the constant tridiagonal (off, diag, off): one thread
+__global__ void thomas_coef_kernel(int nx, double diag, double off, double *cpr) {
+    double c = 0.0;
+    for (int i = 1; i < nx - 1; ++i) {
+        const double m = diag - off * c;
+        c = off / m;
+        cpr[i] = c;
+        cpr[nx + i] = 1.0 / m;
+    }
+}
+
+// np.linalg.solve(A, rhs) along axis 0 for the interior columns of two fields (blockIdx.y), in place (A is diagonally
+// dominant => LAPACK's partial pivoting never swaps, so this is the same elimination)
+__global__ void thomas_axis0_kernel(SlabGeom g, double *x0, double *x1, double off, const double *__restrict__ cpr) {
+    const int j = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= g.ny - 1) return;
+    double *x = blockIdx.y ? x1 : x0;
+    const int nx = g.nx;
+    double d = 0.0;
+    for (int i = 1; i < nx - 1; ++i) {
+        const size_t q = g.v.at(i, j);
+        d = (x[q] - off * d) * cpr[nx + i];
+        x[q] = d;
+    }
+    double xn = 0.0;
+    for (int i = nx - 2; i >= 1; --i) {
+        const size_t q = g.v.at(i, j);
+        xn = x[q] - cpr[i] * xn;
+        x[q] = xn;
+    }
+}
+
+// right-hand side of the second ADI stage (chorin_fd:155-165)
+__global__ void semi_mid_kernel(SlabGeom g, const double *__restrict__ uc, const double *__restrict__ vc,
+                                double *__restrict__ un, double *__restrict__ vn) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = g.row0 + blockIdx.y;
+    if (j < 1 || j >= g.ny - 1 || i < 1 || i >= g.nx - 1) return;
+    const size_t q = g.v.at(i, j);
+    const double ky = 2.0 / g.nu * (g.dy * g.dy);
+    const double u0 = uc[q], v0 = vc[q];
+    un[q] = ky * (un[q] + u0) - g.dt * (uc[q + 1] - 2.0 * u0 + uc[q - 1]);
+    vn[q] = ky * (vn[q] + v0) - g.dt * (vc[q + 1] - 2.0 * v0 + vc[q - 1]);
 }
 
 // one entry of a BC list on the owned rows (boundary.py:34-86); launched in list order
@@ -549,7 +629,7 @@ void slab_free(nns_handle *h) {
     SlabState *S = static_cast<SlabState *>(h->slab);
     if (!S) return;
     if (S->comm && nccl_api()) nccl_api()->CommDestroy(S->comm);
-    cudaFree(S->d_cprime); cudaFree(S->d_p0); cudaFree(S->d_flags);
+    cudaFree(S->d_cprime); cudaFree(S->d_p0); cudaFree(S->d_thomas); cudaFree(S->d_flags);
     for (double *d : S->d_own) cudaFree(d);
     for (int d = 0; d < 2; ++d) if (S->peer_box[d]) cudaIpcCloseMemHandle(S->peer_box[d]);
     cudaFree(S->d_box);
@@ -570,8 +650,9 @@ int slab_unique_id(unsigned char *id128) {
 }
 
 int slab_attach(nns_handle *h, int rank, int nranks, const unsigned char *id128) {
-    if (h->g.batch != 1 || h->g.method != NNS_METHOD_EXPLICIT) {
-        set_error("slab path: batch must be 1 and method explicit");
+    if (nranks > 1 && (h->g.batch != 1 || h->g.method != NNS_METHOD_EXPLICIT)) {
+        set_error("slab path: one grid over several ranks needs batch 1 and the explicit method (the ADI solves of "
+                  "semi_implicit run along axis 0, across the slabs)");
         return NNS_ERR_UNSUPPORTED;
     }
     slab_free(h);
@@ -672,8 +753,22 @@ int slab_step(nns_handle *h, const double *u, const double *v, const double *u1,
     const dim3 blk(128), grd((G.ny + 127) / 128, S->nrows);
     const size_t bytes = sizeof(double) * (size_t)(S->nrows + 2) * G.ny;
     int rc;
-    slab_predictor_kernel<<<grd, blk, 0, st>>>(g, u, v, u1, v1, un, vn);
-    h->launches += 1;
+    if (G.method == NNS_METHOD_SEMI_IMPLICIT) {
+        // single GPU only (slab_attach refuses it for several ranks): whole columns are local
+        if (!S->d_thomas) NNS_CUDA(cudaMalloc(&S->d_thomas, sizeof(double) * 4 * (size_t)G.nx));
+        const double kx = 2.0 / G.nu * (G.dx * G.dx), ky = 2.0 / G.nu * (G.dy * G.dy);
+        const dim3 tg((G.ny + 127) / 128, 2);
+        semi_rhs_kernel<<<grd, blk, 0, st>>>(g, u, v, u1, v1, un, vn);
+        thomas_coef_kernel<<<1, 1, 0, st>>>(G.nx, kx + 2.0 * G.dt, -G.dt, S->d_thomas);
+        thomas_coef_kernel<<<1, 1, 0, st>>>(G.nx, ky + 2.0 * G.dt, -G.dt, S->d_thomas + 2 * G.nx);
+        thomas_axis0_kernel<<<tg, 128, 0, st>>>(g, un, vn, -G.dt, S->d_thomas);
+        semi_mid_kernel<<<grd, blk, 0, st>>>(g, u, v, un, vn);
+        thomas_axis0_kernel<<<tg, 128, 0, st>>>(g, un, vn, -G.dt, S->d_thomas + 2 * G.nx);
+        h->launches += 6;
+    } else {
+        slab_predictor_kernel<<<grd, blk, 0, st>>>(g, u, v, u1, v1, un, vn);
+        h->launches += 1;
+    }
     if ((rc = apply_bc_list(h, g, 0, un, st)) || (rc = apply_bc_list(h, g, 1, vn, st))) return rc;
     if ((rc = exchange_rows(h, S, un, st))) return rc;             // C' needs ui of the row above
     slab_cprime_kernel<<<grd, blk, 0, st>>>(g, un, vn, S->d_cprime);
@@ -712,15 +807,46 @@ int slab_step(nns_handle *h, const double *u, const double *v, const double *u1,
 
 // Single-GPU run() for grids that do not fit the on-chip paths: plain [nx][ny] buffers from the caller are
 // copied into haloed slabs owned by the handle (nranks = 1), stepped, and copied back.
+static int tiled_run_member(nns_handle *h, double *bufU[3], double *bufV[3], double *p, int nsteps, int nsteps_total,
+                            int step0, int fixup, double *tu, double *tv, double *tp, int32_t *sweeps, int sweeps_stride,
+                            cudaStream_t st);
+
+// Single-GPU run() for grids that do not fit the on-chip paths: plain [nx][ny] buffers from the caller are copied into
+// haloed slabs owned by the handle (nranks = 1), stepped, and copied back.  The members of a batch are advanced one
+// after the other (each with its own nu / BC values): a member of this size fills the GPU by itself.
 int chorin_tiled_run(nns_handle *h, double *bufU[3], double *bufV[3], double *p, int nsteps, int nsteps_total,
                      int step0, int phases, int fixup, double *tu, double *tv, double *tp, int32_t *sweeps,
                      cudaStream_t st, int m0, int count) {
-    (void)m0; (void)count; (void)fixup;
-    if (h->g.batch != 1 || h->g.method != NNS_METHOD_EXPLICIT || phases != 7) {
-        set_error("chorin_fd: grid %dx%d does not fit the on-chip path; the tiled path supports batch 1, explicit, "
-                  "whole steps", h->g.nx, h->g.ny);
+    if (phases != 7) {
+        set_error("chorin_fd: grid %dx%d does not fit the on-chip path; the tiled path runs whole steps only (the stage "
+                  "entry points are for unit parity on small grids)", h->g.nx, h->g.ny);
         return NNS_ERR_UNSUPPORTED;
     }
+    if (count < 0) count = h->g.batch - m0;
+    const size_t N = (size_t)h->g.nx * h->g.ny;
+    const double nu0 = h->g.nu;
+    BcList bc0[3] = {h->bc[0], h->bc[1], h->bc[2]};
+    int rc = NNS_OK;
+    for (int mm = 0; mm < count && rc == NNS_OK; ++mm) {
+        const int m = m0 + mm;
+        if (h->h_nu) h->g.nu = h->h_nu[m];
+        if (h->h_bcval)
+            for (int f = 0; f < 3; ++f)
+                for (int k = 0; k < h->bc[f].n; ++k) h->bc[f].value[k] = h->h_bcval[(size_t)m * h->n_bcs + h->bc[f].slot[k]];
+        double *U[3] = {bufU[0] + mm * N, bufU[1] + mm * N, bufU[2] + mm * N};
+        double *V[3] = {bufV[0] + mm * N, bufV[1] + mm * N, bufV[2] + mm * N};
+        rc = tiled_run_member(h, U, V, p + mm * N, nsteps, nsteps_total, step0, fixup,
+                              tu ? tu + (size_t)mm * nsteps_total * N : nullptr, tv ? tv + (size_t)mm * nsteps_total * N : nullptr,
+                              tp ? tp + (size_t)mm * nsteps_total * N : nullptr, sweeps ? sweeps + mm : nullptr, h->g.batch, st);
+    }
+    h->g.nu = nu0;
+    for (int f = 0; f < 3; ++f) h->bc[f] = bc0[f];
+    return rc;
+}
+
+static int tiled_run_member(nns_handle *h, double *bufU[3], double *bufV[3], double *p, int nsteps, int nsteps_total,
+                            int step0, int fixup, double *tu, double *tv, double *tp, int32_t *sweeps, int sweeps_stride,
+                            cudaStream_t st) {
     int rc;
     if (!h->slab && (rc = slab_attach(h, 0, 1, nullptr))) return rc;
     SlabState *S = static_cast<SlabState *>(h->slab);
@@ -739,7 +865,7 @@ int chorin_tiled_run(nns_handle *h, double *bufU[3], double *bufV[3], double *p,
     for (int n = 0; n < nsteps; ++n) {
         int32_t need = 0;
         if ((rc = slab_step(h, U[cur], V[cur], U[prev], V[prev], Ps, U[nxt], V[nxt], &need, st))) return rc;
-        if (sweeps) NNS_CUDA(cudaMemcpyAsync(sweeps + (size_t)(step0 + n) * h->g.batch, &need, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        if (sweeps) NNS_CUDA(cudaMemcpyAsync(sweeps + (size_t)(step0 + n) * sweeps_stride, &need, sizeof(int32_t), cudaMemcpyHostToDevice, st));
         if (tu) {
             const size_t off = (size_t)(step0 + n) * N;
             NNS_CUDA(cudaMemcpyAsync(tu + off, U[nxt] + ny, nb, cudaMemcpyDeviceToDevice, st));

@@ -35,6 +35,7 @@ struct nns_handle {
     int n_bcs;                // total entries (per-member value table width)
     double *d_nu;             // [batch] or nullptr
     double *d_bcval;          // [batch][n_bcs] or nullptr
+    double *h_nu, *h_bcval;   // host copies of the two (the tiled path steps the members of a batch one after the other)
     double *d_scratch[4];     // rotation / ui,vi workspace, [batch][nx][ny] each, lazily allocated
     double *d_stage[7];       // device staging of the host-buffer entry points
     void *d_pool[10];         // cached device buffers of the *_run_host entry points (fields, trajectories, sweeps)

@@ -131,3 +131,49 @@ def test_slabs_over_gpus_vs_oracle(oracle_fd, world):
                                                dt=1e-4, rho=1, nu=0.05, beta=1.25)
     assert rel_l2(u, ou[-1]) <= TOL and rel_l2(v, ov[-1]) <= TOL and rel_l2(p, op[-1]) <= TOL
     assert sws == list(sw)
+
+
+def test_ensemble_beyond_one_sm_vs_oracle(oracle_fd, monkeypatch):
+    """ChorinEnsemble on a grid that fits neither the 128 x 128 stream kernel nor one SM (200 x 260): the members of
+    the batch go through the tiled path one after the other, each with its own nu and lid value; smooth start, 2 steps
+    with trajectories and sweep counts against the oracle (rel-L2 <= 1e-10, counts exact)."""
+    monkeypatch.delenv("NNS_CHIP_MODE", raising=False)
+    from nns_b200.ensemble import ChorinEnsemble, cavity_bc_values, cavity_bcs
+    B, nx, ny = 3, 200, 260
+    dx, dy = 2. / (nx - 1), 2. / (ny - 1)
+    u_bc, v_bc, p_bc = cavity_bcs(dx, dy)
+    lid, nu = np.array([0.7, 1.0, 1.3]), np.array([0.02, 0.05, 0.1])
+    ics = [smooth_ic(nx, ny, 70 + b, amp=0.05) for b in range(B)]
+    ens = ChorinEnsemble(B, nx, ny, u_bc=u_bc, v_bc=v_bc, p_bc=p_bc, nit=12, dt=2e-5, rho=1, nu=nu, beta=1.25,
+                         method='explicit', bc_values=cavity_bc_values(lid))
+    ens.set_state(np.stack([c[0] for c in ics]), np.stack([c[1] for c in ics]), np.stack([c[2] for c in ics]))
+    ens.init_variables()
+    tu, tv, tp, sw = ens.run(2, trajectory=True, sweeps=True)
+    for b in range(B):
+        ub = [(bc.boundary, bc.type, float(bc.value)) for bc in u_bc]
+        ub[1] = ("right", "dirichlet", float(lid[b]))
+        ou, ov, op, osw = oracle_fd.chorin_simulate(ics[b][0], ics[b][1], ics[b][2], ub, v_bc, p_bc, nt=2, nit=12, dt=2e-5,
+                                                    rho=1, nu=float(nu[b]), beta=1.25)
+        for n in range(2):
+            assert rel_l2(tu[b, n].cpu().numpy(), ou[n]) <= 1e-10 and rel_l2(tv[b, n].cpu().numpy(), ov[n]) <= 1e-10
+            assert rel_l2(tp[b, n].cpu().numpy(), op[n]) <= 1e-10
+        assert list(sw[:, b].cpu().numpy()) == list(osw)
+
+
+def test_semi_implicit_beyond_one_sm_vs_oracle(oracle_fd):
+    """method='semi_implicit' (the reference's default) on a 200 x 200 grid, which does not fit one SM: predictor by
+    column-parallel Thomas solves along axis 0 in HBM + the tiled SOR; drop-in class, 3 steps against the oracle."""
+    from nns_b200.chorin_fd.simulate import NavierStokesSystem
+    from nns_b200.ensemble import cavity_bcs
+    nx = ny = 200
+    dx = dy = 2. / (nx - 1)
+    u_bc, v_bc, p_bc = cavity_bcs(dx, dy)
+    u0, v0, p0 = smooth_ic(nx, ny, 9, amp=0.05)
+    s = NavierStokesSystem(u0, v0, p0, u_bc, v_bc, p_bc, nt=3, nit=15, nx=nx, ny=ny, dt=5e-5, rho=1, nu=0.1, beta=1.25,
+                           method='semi_implicit')
+    u, v, p = s.simulate()
+    ou, ov, op, osw = oracle_fd.chorin_simulate(u0, v0, p0, u_bc, v_bc, p_bc, nt=3, nit=15, dt=5e-5, rho=1, nu=0.1,
+                                                beta=1.25, method='semi_implicit')
+    for n in range(3):
+        assert rel_l2(u[n], ou[n]) <= 1e-10 and rel_l2(v[n], ov[n]) <= 1e-10 and rel_l2(p[n], op[n]) <= 1e-10, n
+    assert list(s.last_sweeps) == list(osw)
