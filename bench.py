@@ -40,6 +40,10 @@ SLAB_WORKLOADS = {
     "slab_cavity16384": (16384, 16384, 50, 1e-8, 0.1),
     "slab_cavity4096": (4096, 4096, 50, 1.5e-7, 0.1),
 }
+# direct_fd (Jacobi) on row slabs: name -> (nx, ny, nit, dt, nu)
+DIRECT_SLAB_WORKLOADS = {
+    "direct_slab8192": (8192, 8192, 50, 1e-8, 0.1),
+}
 BYTES_PER_CELL_SWEEP = 24       # read p, read C', write p in an un-blocked sweep
 
 
@@ -260,6 +264,66 @@ def slab_measure(workload, steps, warmup, rank, world, local, with_clocks=True):
     return out
 
 
+def run_direct_slab(args, rank, world, local):
+    """One large direct_fd grid on row slabs (strong scaling): a step = RHS + nit Jacobi sweeps (one halo row of p per
+    sweep over NCCL) + velocity update."""
+    import torch
+    import torch.distributed as dist
+    from nns_b200.ensemble import cavity_bcs
+    from nns_b200.slab import SlabDirect
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nx, ny, nit, dt, nu = DIRECT_SLAB_WORKLOADS[args.workload]
+    u_bc, v_bc, p_bc = cavity_bcs(2. / (nx - 1), 2. / (ny - 1))
+    sl = SlabDirect(nx, ny, u_bc=u_bc, v_bc=v_bc, p_bc=p_bc, nit=nit, dt=dt, rho=1, nu=nu)
+    sl.sync_halos()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sl.run(args.warmup)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = sl.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sl.run(args.steps)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    finite = bool(torch.isfinite(sl.u).all() and torch.isfinite(sl.p).all())
+    if rank == 0:
+        peak, peak_src = peaks()
+        cells = nx * ny
+        fused = 48 * cells / (ms_total / args.steps * 1e-3) / 1e9
+        unblocked = (24 * nit + 120) * (cells / world) / (ms_total / args.steps * 1e-3) / 1e9
+        print(json.dumps({
+            "metric": METRIC, "value": cells * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "solver": "direct_fd", "nx": nx, "ny": ny, "nit": nit, "dt": dt, "nu": nu,
+                       "parallelism": "row slabs, one halo row of p per Jacobi sweep (NCCL send/recv)",
+                       "l2": "p + b per GPU %.2f GB >> 126 MB L2" % (2 * cells * 8 / world / 1e9), "finite": finite},
+            "e2e": None, "gpu_launches": int(sl.launches - l0), "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": fused, "peak": peak, "unit": "GB/s", "frac": fused / peak, "traffic": None,
+                         "peak_source": peak_src, "kernel": "direct_fd slab step", "bytes_per_cell_update": 48,
+                         "unblocked": {"achieved_per_gpu": unblocked, "frac_per_gpu": unblocked / peak,
+                                       "bytes_per_cell_update": 24 * nit + 120},
+                         "note": "frac: fully fused model (48 B per cell-update); unblocked: the sweeps as implemented "
+                                 "(24 B per cell and sweep + RHS and update passes)"}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_slab(args, rank, world, local):
     import torch
     import torch.distributed as dist
@@ -429,7 +493,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="ensemble4096_cavity128", choices=sorted(WORKLOADS) + sorted(SLAB_WORKLOADS))
+    ap.add_argument("--workload", default="ensemble4096_cavity128",
+                    choices=sorted(WORKLOADS) + sorted(SLAB_WORKLOADS) + sorted(DIRECT_SLAB_WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--members", type=int, default=None, help="override members per GPU")
@@ -440,6 +505,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload in DIRECT_SLAB_WORKLOADS:
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "slab workloads have no CPU arm; use the default workload"}))
+            return
+        run_direct_slab(args, rank, world, local)
+        return
     if args.workload in SLAB_WORKLOADS:
         if args.impl == "reference":
             if rank == 0:

@@ -228,6 +228,12 @@ int32_t nns_chorin_fd_slab_step(nns_handle *h, const double *u, const double *v,
 /* Device time (CUDA events) of the SOR tick loop of the last step and its number of ticks (= sweep-kernel launches). */
 int32_t nns_slab_last_timing(nns_handle *h, float *sor_ms, int32_t *ticks);
 
+/* direct_fd on row slabs (src/direct_fd/simulate.py:56-127; one grid over the GPUs of a box): nsteps of step() on the
+ * local slabs u, v, p ([nrows + 2][ny], halo rows valid on entry and on return; nns_slab_attach / nns_slab_apply_bc /
+ * nns_slab_exchange as for chorin_fd).  Jacobi has no ordering dependency: every sweep is one kernel on the owned rows, the
+ * p BCs and one halo-row exchange with the neighbouring ranks. */
+int32_t nns_direct_fd_slab_run(nns_handle *h, double *u, double *v, double *p, int32_t nsteps, void *stream);
+
 /* ---- trajectory sink (the interface between the time-step path and the rest of the reference) ---- */
 
 /* Block means of device trajectories, replaces utils.spatial_coarsen (src/utils.py:13-60) for the u, v, p

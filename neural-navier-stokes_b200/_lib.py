@@ -61,6 +61,7 @@ _PROTOS = {
     "nns_slab_ipc_export": (_i32, [_vp, _vp]),
     "nns_slab_ipc_connect": (_i32, [_vp, _vp, _vp]),
     "nns_chorin_fd_slab_step": (_i32, [_vp] * 10),
+    "nns_direct_fd_slab_run": (_i32, [_vp] * 4 + [_i32, _vp]),
     "nns_slab_last_timing": (_i32, [_vp, C.POINTER(C.c_float), C.POINTER(_i32)]),
     "nns_traj_coarsen": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "nns_traj_observations": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),

@@ -48,6 +48,7 @@ int slab_exchange(nns_handle *h, double *f, cudaStream_t st);
 int slab_last_timing(nns_handle *h, float *sor_ms, int *ticks);
 int slab_ipc_export(nns_handle *h, unsigned char *handle64);
 int slab_ipc_connect(nns_handle *h, const unsigned char *above64, const unsigned char *below64);
+int direct_slab_run(nns_handle *h, double *u, double *v, double *p, int nsteps, cudaStream_t st);
 int slab_step(nns_handle *h, const double *u, const double *v, const double *u1, const double *v1, double *p,
               double *un, double *vn, int32_t *sweeps_host, cudaStream_t st);
 // direct_fd.cu
@@ -549,6 +550,16 @@ int32_t nns_spectral_run_host(nns_handle *h, double *u, double *v, double *u1, d
 
 // ---- chorin_fd on row slabs (one grid over several GPUs) ---------------------------------------
 
+#define NNS_CHECK_SLAB_HANDLE(h)                                                                                     \
+    do {                                                                                                              \
+        if (!(h)) { set_error("null handle"); return NNS_ERR_INVALID; }                                               \
+        if ((h)->params.solver != NNS_SOLVER_CHORIN_FD && (h)->params.solver != NNS_SOLVER_DIRECT_FD) {               \
+            set_error("row slabs exist for chorin_fd and direct_fd (handle was created for solver %d)", (h)->params.solver); \
+            return NNS_ERR_INVALID;                                                                                   \
+        }                                                                                                             \
+        NNS_CUDA(cudaSetDevice((h)->device));                                                                         \
+    } while (0)
+
 int32_t nns_slab_partition(int32_t nx, int32_t nranks, int32_t rank, int32_t tile_rows, int32_t *row0, int32_t *nrows) {
     return slab_partition(nx, nranks, rank, tile_rows, row0, nrows, nullptr, nullptr, nullptr);
 }
@@ -560,7 +571,7 @@ int32_t nns_slab_plan(int32_t nx, int32_t ny, int32_t nranks, int32_t rank, int3
 }
 
 int32_t nns_slab_apply_bc(nns_handle *h, int32_t field, double *a, void *stream) {
-    NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_FD);
+    NNS_CHECK_SLAB_HANDLE(h);
     if (!a || field < 0 || field > 2) { set_error("nns_slab_apply_bc: bad argument"); return NNS_ERR_INVALID; }
     return slab_apply_bc(h, field, a, (cudaStream_t)stream);
 }
@@ -571,13 +582,13 @@ int32_t nns_nccl_unique_id(uint8_t *id128) {
 }
 
 int32_t nns_slab_attach(nns_handle *h, int32_t rank, int32_t nranks, const uint8_t *id128) {
-    NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_FD);
+    NNS_CHECK_SLAB_HANDLE(h);
     if (nranks < 1 || rank < 0 || rank >= nranks) { set_error("nns_slab_attach: bad rank %d of %d", rank, nranks); return NNS_ERR_INVALID; }
     return slab_attach(h, rank, nranks, id128);
 }
 
 int32_t nns_slab_exchange(nns_handle *h, double *field, void *stream) {
-    NNS_CHECK_HANDLE(h, NNS_SOLVER_CHORIN_FD);
+    NNS_CHECK_SLAB_HANDLE(h);
     if (!field) { set_error("nns_slab_exchange: null field"); return NNS_ERR_INVALID; }
     return slab_exchange(h, field, (cudaStream_t)stream);
 }
@@ -605,6 +616,14 @@ int32_t nns_chorin_fd_slab_step(nns_handle *h, const double *u, const double *v,
     if (!u || !v || !u1 || !v1 || !p || !u_out || !v_out) { set_error("nns_chorin_fd_slab_step: null field"); return NNS_ERR_INVALID; }
     if (u_out == u || u_out == u1 || v_out == v || v_out == v1) { set_error("nns_chorin_fd_slab_step: outputs alias inputs"); return NNS_ERR_INVALID; }
     return slab_step(h, u, v, u1, v1, p, u_out, v_out, sweeps_out_host, (cudaStream_t)stream);
+}
+
+int32_t nns_direct_fd_slab_run(nns_handle *h, double *u, double *v, double *p, int32_t nsteps, void *stream) {
+    NNS_CHECK_HANDLE(h, NNS_SOLVER_DIRECT_FD);
+    if (!u || !v || !p || nsteps < 0) { set_error("nns_direct_fd_slab_run: bad argument"); return NNS_ERR_INVALID; }
+    if (h->params.flags & NNS_FLAG_PERIODIC_X) { set_error("nns_direct_fd_slab_run: the periodic-x extension is not available on slabs"); return NNS_ERR_UNSUPPORTED; }
+    if (nsteps == 0) return NNS_OK;
+    return direct_slab_run(h, u, v, p, nsteps, (cudaStream_t)stream);
 }
 
 }  // extern "C"

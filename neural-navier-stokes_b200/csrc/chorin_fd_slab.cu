@@ -650,7 +650,7 @@ int slab_unique_id(unsigned char *id128) {
 }
 
 int slab_attach(nns_handle *h, int rank, int nranks, const unsigned char *id128) {
-    if (nranks > 1 && (h->g.batch != 1 || h->g.method != NNS_METHOD_EXPLICIT)) {
+    if (nranks > 1 && (h->g.batch != 1 || (h->params.solver == NNS_SOLVER_CHORIN_FD && h->g.method != NNS_METHOD_EXPLICIT))) {
         set_error("slab path: one grid over several ranks needs batch 1 and the explicit method (the ADI solves of "
                   "semi_implicit run along axis 0, across the slabs)");
         return NNS_ERR_UNSUPPORTED;
@@ -807,6 +807,105 @@ int slab_step(nns_handle *h, const double *u, const double *v, const double *u1,
 
 // Single-GPU run() for grids that do not fit the on-chip paths: plain [nx][ny] buffers from the caller are
 // copied into haloed slabs owned by the handle (nranks = 1), stepped, and copied back.
+// ---- direct_fd on row slabs (src/direct_fd/simulate.py:56-127; one grid over several GPUs) ------------------------------
+// Jacobi has no ordering dependency: every sweep is one kernel on the owned rows, the p BCs, and one halo-row exchange
+// with the neighbouring ranks (NCCL send / recv of single rows); u, v swap halo rows once per step.  Same expressions
+// per cell as direct_fd.cu (axis 1 <-> dx, axis 0 <-> dy: the transpose of boundary.py, as in the reference).
+__global__ void dslab_rhs_kernel(SlabGeom g, const double *__restrict__ u, const double *__restrict__ v, double *__restrict__ b) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = g.row0 + blockIdx.y;
+    if (j >= g.ny || i >= g.row1) return;
+    const size_t q = g.v.at(i, j);
+    const int ny = g.ny;
+    const double dx2 = g.dx * g.dx, dy2 = g.dy * g.dy;
+    const double kb = dx2 * dy2 / (2.0 * (dx2 + dy2));
+    double bb = 0.0;
+    if (i > 0 && i < g.nx - 1 && j > 0 && j < ny - 1) {
+        const double r2dx = 1.0 / (2.0 * g.dx), r2dy = 1.0 / (2.0 * g.dy);
+        const double ux = (u[q + 1] - u[q - 1]) * r2dx, vy = (v[q + ny] - v[q - ny]) * r2dy;
+        const double uy = (u[q + ny] - u[q - ny]) * r2dy, vx = (v[q + 1] - v[q - 1]) * r2dx;
+        bb = g.rho * ((1.0 / g.dt) * (ux + vy)) - ux * ux - 2.0 * (uy * vx) - vy * vy;
+    }
+    b[q] = kb * bb;
+}
+
+__global__ void dslab_jacobi_kernel(SlabGeom g, const double *__restrict__ pc, const double *__restrict__ bs, double *__restrict__ pn) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = g.row0 + blockIdx.y;
+    if (j >= g.ny || i >= g.row1) return;
+    const size_t q = g.v.at(i, j);
+    const int ny = g.ny;
+    const double dx2 = g.dx * g.dx, dy2 = g.dy * g.dy;
+    const double rden = 1.0 / (2.0 * (dx2 + dy2));
+    double r = pc[q];
+    if (i > 0 && i < g.nx - 1 && j > 0 && j < ny - 1)
+        r = (pc[q + 1] + pc[q - 1]) * (dy2 * rden) + (pc[q + ny] + pc[q - ny]) * (dx2 * rden) - bs[q];
+    pn[q] = r;
+}
+
+__global__ void dslab_update_kernel(SlabGeom g, const double *__restrict__ uo, const double *__restrict__ vo,
+                                    const double *__restrict__ p, double *__restrict__ un, double *__restrict__ vn,
+                                    unsigned long long *nonfinite, int check) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = g.row0 + blockIdx.y;
+    if (j >= g.ny || i >= g.row1) return;
+    const size_t q = g.v.at(i, j);
+    const int ny = g.ny;
+    const double dt = g.dt, dx = g.dx, dy = g.dy, rho = g.rho, nu = g.nu;
+    const double uc = uo[q], vc = vo[q];
+    double ru = uc, rv = vc;
+    if (i > 0 && i < g.nx - 1 && j > 0 && j < ny - 1) {
+        const double kpx = dt / (2.0 * rho * dx), kpy = dt / (2.0 * rho * dy);
+        const double kdx = dt / (dx * dx), kdy = dt / (dy * dy), ax = dt / dx, ay = dt / dy;
+        const double uW = uo[q - 1], uE = uo[q + 1], uN = uo[q - ny], uS = uo[q + ny];
+        const double vW = vo[q - 1], vE = vo[q + 1], vN = vo[q - ny], vS = vo[q + ny];
+        ru = uc - uc * ax * (uc - uW) - vc * ay * (uc - uN) - kpx * (p[q + 1] - p[q - 1]) +
+             nu * (kdx * (uE - 2.0 * uc + uW) + kdy * (uS - 2.0 * uc + uN));
+        rv = vc - uc * ax * (vc - vW) - vc * ay * (vc - vN) - kpy * (p[q + ny] - p[q - ny]) +
+             nu * (kdx * (vE - 2.0 * vc + vW) + kdy * (vS - 2.0 * vc + vN));
+    }
+    un[q] = ru;
+    vn[q] = rv;
+    if (check && !(isfinite(ru) && isfinite(rv))) atomicAdd(nonfinite, 1ull);
+}
+
+// nsteps of step() on the local slabs ([nrows + 2][ny] each; halo rows of u, v, p valid on entry and on return).
+int direct_slab_run(nns_handle *h, double *u, double *v, double *p, int nsteps, cudaStream_t st) {
+    SlabState *S = static_cast<SlabState *>(h->slab);
+    if (!S) { set_error("slab path: call nns_slab_attach first"); return NNS_ERR_INVALID; }
+    const Geometry &G = h->g;
+    SlabGeom g{};
+    g.nx = G.nx; g.ny = G.ny; g.row0 = S->row0; g.row1 = S->row0 + S->nrows;
+    g.v.rowbase = S->row0 - 1; g.v.ny = G.ny;
+    g.dt = G.dt; g.dx = G.dx; g.dy = G.dy; g.rho = G.rho; g.nu = G.nu; g.beta = G.beta; g.tol = G.tol;
+    const dim3 blk(128), grd((G.ny + 127) / 128, S->nrows);
+    const size_t bytes = sizeof(double) * (size_t)(S->nrows + 2) * G.ny;
+    for (int k = 0; k < 4; ++k)
+        if (!S->d_own[k]) { NNS_CUDA(cudaMalloc(&S->d_own[k], bytes)); NNS_CUDA(cudaMemsetAsync(S->d_own[k], 0, bytes, st)); }
+    double *uc = u, *vc = v, *un = S->d_own[0], *vn = S->d_own[1], *pn = S->d_own[2], *b = S->d_own[3], *pc = p;
+    int rc;
+    for (int n = 0; n < nsteps; ++n) {
+        dslab_rhs_kernel<<<grd, blk, 0, st>>>(g, uc, vc, b);
+        for (int s = 0; s < G.nit; ++s) {
+            dslab_jacobi_kernel<<<grd, blk, 0, st>>>(g, pc, b, pn);
+            h->launches += 1;
+            if ((rc = apply_bc_list(h, g, 2, pn, st)) || (rc = exchange_rows(h, S, pn, st))) return rc;
+            double *t = pc; pc = pn; pn = t;
+        }
+        dslab_update_kernel<<<grd, blk, 0, st>>>(g, uc, vc, pc, un, vn, h->d_nonfinite, h->params.flags & NNS_FLAG_CHECK_FINITE);
+        h->launches += 2;
+        if ((rc = apply_bc_list(h, g, 0, un, st)) || (rc = apply_bc_list(h, g, 1, vn, st))) return rc;
+        if ((rc = exchange_rows(h, S, un, st)) || (rc = exchange_rows(h, S, vn, st))) return rc;
+        double *t;
+        t = uc; uc = un; un = t;
+        t = vc; vc = vn; vn = t;
+    }
+    NNS_CUDA(cudaGetLastError());
+    if (pc != p) NNS_CUDA(cudaMemcpyAsync(p, pc, bytes, cudaMemcpyDeviceToDevice, st));
+    if (uc != u) {
+        NNS_CUDA(cudaMemcpyAsync(u, uc, bytes, cudaMemcpyDeviceToDevice, st));
+        NNS_CUDA(cudaMemcpyAsync(v, vc, bytes, cudaMemcpyDeviceToDevice, st));
+    }
+    return NNS_OK;
+}
+
 static int tiled_run_member(nns_handle *h, double *bufU[3], double *bufV[3], double *p, int nsteps, int nsteps_total,
                             int step0, int fixup, double *tu, double *tv, double *tp, int32_t *sweeps, int sweeps_stride,
                             cudaStream_t st);

@@ -131,3 +131,54 @@ class SlabChorin:
     @property
     def launches(self):
         return self.handle.launches
+
+
+class SlabDirect:
+    """direct_fd (src/direct_fd/simulate.py) on this rank's row slab of an (nx, ny) grid: Jacobi sweeps with one halo-row
+    exchange per sweep (NCCL over NVLink).  u, v, p are advanced in place, as the reference does."""
+
+    def __init__(self, nx, ny, *, u_bc, v_bc, p_bc, nit=50, dt=0.001, rho=1, nu=0.1, rank=None, world=None, device=None,
+                 check_finite=False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("nns_b200 slabs need a CUDA device (no CPU fallback)")
+        import torch.distributed as dist
+        if rank is None:
+            rank = dist.get_rank() if dist.is_initialized() else 0
+            world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank, self.world, self.nx, self.ny = rank, world, nx, ny
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.handle = _lib.Handle(_lib.SOLVER_DIRECT_FD, nx, ny, nit, dt, rho, nu, batch=1, u_bc=u_bc, v_bc=v_bc, p_bc=p_bc,
+                                  device=self.device.index, check_finite=check_finite)
+        self._L = _lib.lib()
+        idbuf = np.zeros(128, dtype=np.uint8)
+        if world > 1:
+            if rank == 0:
+                _lib.check(self._L.nns_nccl_unique_id(idbuf.ctypes.data))
+            box = [idbuf.tobytes()]
+            dist.broadcast_object_list(box, src=0)
+            idbuf = np.frombuffer(box[0], dtype=np.uint8).copy()
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.nns_slab_attach(self.handle.h, rank, world, idbuf.ctypes.data))
+        self.row0, self.nrows = partition(nx, world, rank)
+        z = lambda: torch.zeros((self.nrows + 2, ny), dtype=torch.float64, device=self.device)  # noqa: E731
+        self.u, self.v, self.p = z(), z(), z()
+
+    _stream = SlabChorin._stream
+    owned = SlabChorin.owned
+    set_state = SlabChorin.set_state
+    exchange = SlabChorin.exchange
+    gather = SlabChorin.gather
+
+    def sync_halos(self):
+        """Halo rows of u, v, p from the neighbouring ranks (once after set_state; the reference applies no BCs before
+        step 0, direct_fd/simulate.py:132)."""
+        for t in (self.u, self.v, self.p):
+            self.exchange(t)
+
+    def run(self, nsteps):
+        _lib.check(self._L.nns_direct_fd_slab_run(self.handle.h, self.u.data_ptr(), self.v.data_ptr(), self.p.data_ptr(),
+                                                  nsteps, self._stream()))
+
+    @property
+    def launches(self):
+        return self.handle.launches

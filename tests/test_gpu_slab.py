@@ -177,3 +177,57 @@ def test_semi_implicit_beyond_one_sm_vs_oracle(oracle_fd):
     for n in range(3):
         assert rel_l2(u[n], ou[n]) <= 1e-10 and rel_l2(v[n], ov[n]) <= 1e-10 and rel_l2(p[n], op[n]) <= 1e-10, n
     assert list(s.last_sweeps) == list(osw)
+
+
+def _direct_rank_main(rank, world, port, nx, ny, nsteps, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    from nns_b200.slab import SlabDirect
+    u_bc, v_bc, p_bc = _bcs(nx, ny, "mixed")
+    ic = smooth_ic(nx, ny, 33, amp=0.1)
+    sl = SlabDirect(nx, ny, u_bc=u_bc, v_bc=v_bc, p_bc=p_bc, nit=9, dt=1e-4, rho=1.1, nu=0.05)
+    sl.set_state(*ic)
+    sl.sync_halos()
+    sl.run(nsteps)
+    u, v, p = sl.gather(sl.u), sl.gather(sl.v), sl.gather(sl.p)
+    if rank == 0:
+        q.put((u, v, p))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_direct_fd_slabs_vs_oracle(oracle_fd, world):
+    """direct_fd on row slabs (one halo row of p per Jacobi sweep over NCCL; u, v once per step), 130 x 200, mixed BC
+    order, 3 steps (an odd number: the ping-pong copy-back), against the oracle; world = 1 runs the same kernels without
+    a communicator."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    nx, ny, nsteps = 130, 200, 3
+    u_bc, v_bc, p_bc = _bcs(nx, ny, "mixed")
+    ic = smooth_ic(nx, ny, 33, amp=0.1)
+    if world == 1:
+        from nns_b200.slab import SlabDirect
+        sl = SlabDirect(nx, ny, u_bc=u_bc, v_bc=v_bc, p_bc=p_bc, nit=9, dt=1e-4, rho=1.1, nu=0.05, rank=0, world=1)
+        sl.set_state(*ic)
+        sl.sync_halos()
+        sl.run(nsteps)
+        u, v, p = sl.gather(sl.u), sl.gather(sl.v), sl.gather(sl.p)
+    else:
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_direct_rank_main, args=(r, world, port, nx, ny, nsteps, q)) for r in range(world)]
+        for pr in procs:
+            pr.start()
+        u, v, p = q.get(timeout=600)
+        for pr in procs:
+            pr.join(timeout=120)
+    ou, ov, op = oracle_fd.direct_simulate(ic[0].copy(), ic[1].copy(), ic[2].copy(), _t(u_bc), _t(v_bc), _t(p_bc), nt=nsteps,
+                                           nit=9, dt=1e-4, rho=1.1, nu=0.05)
+    assert rel_l2(u, ou[-1]) <= TOL and rel_l2(v, ov[-1]) <= TOL and rel_l2(p, op[-1]) <= TOL
