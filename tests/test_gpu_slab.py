@@ -109,7 +109,7 @@ def _rank_main(rank, world, port, nx, ny, nsteps, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_slabs_over_gpus_vs_oracle(oracle_fd, world):
     import torch
     import torch.multiprocessing as mp
@@ -199,7 +199,7 @@ def _direct_rank_main(rank, world, port, nx, ny, nsteps, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [1, 2, 4])
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
 def test_direct_fd_slabs_vs_oracle(oracle_fd, world):
     """direct_fd on row slabs (one halo row of p per Jacobi sweep over NCCL; u, v once per step), 130 x 200, mixed BC
     order, 3 steps (an odd number: the ping-pong copy-back), against the oracle; world = 1 runs the same kernels without
