@@ -34,7 +34,11 @@ constexpr int GRW = 8;          // rows per ring group of the wave kernel (measu
 constexpr int NG = 2;           // groups in the ring of the legacy kernel (double buffer)
 constexpr int NGW = 4;          // groups in the ring of the wave kernel (C' lives in Tensor Memory: room for a deep ring)
 constexpr int RING = GR * NG;   // rows per field in the stencil ring
-constexpr int REGS_SOR = 200, REGS_ST = 104;
+#ifndef NNS_REGS_SOR
+#define NNS_REGS_SOR 192     // 8 x 32 x 192 + 4 x 32 x 120 = 64512 = 384 x 168 (the CTA's allocation)
+#define NNS_REGS_ST 120
+#endif
+constexpr int REGS_SOR = NNS_REGS_SOR, REGS_ST = NNS_REGS_ST;
 constexpr int REGS_SOR_W = 200, REGS_ST_W = 104;     // setmaxnreg only moves registers inside the CTA's launch allocation (384 x 168)
 constexpr int NW_SOR = NT_SOR / 32;
 constexpr int N_SCRATCH = 4;    // per-CTA scratch sets: launches on different internal streams (nns_chorin_fd_step_host) may overlap
@@ -82,6 +86,7 @@ struct StreamArgs {
 
 // phase timers: thread `lead` of a role accumulates clock64() deltas into prof[slot]
 constexpr int NPROF = 32;
+constexpr int TRACE_STAGES = 160;   // NNS_STREAM_TRACE builds: stage trace of CTA 0, second member
 #ifdef NNS_STREAM_PROF_FINE      // timers inside the stencil passes: they cost registers even when switched off at run time
 #define NNS_FINE(...) __VA_ARGS__
 #else
@@ -123,6 +128,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(b))
                  : "memory");
 }
+// 1-D bulk copy shared -> global (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_all() {
+    asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group 0;" ::: "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
@@ -143,7 +155,8 @@ __constant__ short c_ord[128];     // diag_ord of cell q = li * BC + lj (host-fi
 template <int BR, int BC, int RS, int TRACK>
 __device__ __forceinline__ void wavefront(double (&P)[BR][BC], const double2 *Cme, const SHalo<BR, BC> &h, bool owner,
                                           int sd, int tmax, int cap, const Coef &k, unsigned long long tolbits,
-                                          unsigned long long &mask, unsigned long long &amb, long long *prof = nullptr) {
+                                          unsigned long long &mask, unsigned long long &amb, long long *prof = nullptr,
+                                          long long *trace = nullptr) {
     if (owner) publish<BR, BC, 0, BR>(P, h);   // the whole perimeter once
     named_sync(BAR_SOR, NT_SOR);
     const unsigned tolhi = (unsigned)(tolbits >> 32);
@@ -154,14 +167,23 @@ __device__ __forceinline__ void wavefront(double (&P)[BR][BC], const double2 *Cm
     for (int T = 0; T <= tmax; ++T) {
         const int q = T - sd;                       // 2s for the top sub-block, 2s + 1 for the bottom one
         const bool work = owner && q >= 0 && q <= 2 * (cap - 1) + 1;
+#ifdef NNS_STREAM_TRACE
+        const unsigned nact = __popc(__ballot_sync(0xffffffffu, work));
+        if (trace && (threadIdx.x & 31) == 0 && T < TRACE_STAGES) { trace[T * 4 + 0] = clock64(); trace[T * 4 + 2] = nact; }
+#endif
         if (work) {
             unsigned mhi = 0u;
             bool v = false;
 #ifdef NNS_STREAM_PROF_SWEEP
             const long long ts0 = prof ? clock64() : 0ll;
 #endif
+#ifdef NNS_SOR_PFD       // experiment: explicit C' prefetch distance (anti-diagonals)
+            if (!(q & 1)) block_sweep_pf<BR, BC, RS, 0, RS, TRACK, NNS_SOR_PFD>(P, Cme, h, k, tolbits, mhi, v);
+            else block_sweep_pf<BR, BC, RS, RS, BR, TRACK, NNS_SOR_PFD>(P, Cme, h, k, tolbits, mhi, v);
+#else
             if (!(q & 1)) block_sweep<BR, BC, RS, 0, RS, TRACK>(P, Cme, h, k, tolbits, mhi, v);
             else block_sweep<BR, BC, RS, RS, BR, TRACK>(P, Cme, h, k, tolbits, mhi, v);
+#endif
 #ifdef NNS_STREAM_PROF_SWEEP
             if (prof) { prof[0] += clock64() - ts0; prof[1] += 1; }
 #endif
@@ -172,7 +194,14 @@ __device__ __forceinline__ void wavefront(double (&P)[BR][BC], const double2 *Cm
                 mask |= (unsigned long long)v << (q >> 1);
             }
         }
+#ifdef NNS_STREAM_TRACE
+        __syncwarp();
+        if (trace && (threadIdx.x & 31) == 0 && T < TRACE_STAGES) trace[T * 4 + 1] = clock64();
+#endif
         named_sync(BAR_SOR, NT_SOR);
+#ifdef NNS_STREAM_TRACE
+        if (trace && (threadIdx.x & 31) == 0 && T < TRACE_STAGES) trace[T * 4 + 3] = clock64();
+#endif
     }
 }
 
@@ -353,9 +382,34 @@ __device__ void stencil_pass1(const StreamArgs &a, Ring<C::NY, NGR, GR> &ring, c
         }
         ru_prev = ru;
     };
+#ifndef NNS_ST_BRANCHY
+    // rows 1 .. NX-2 without a branch (every group but the first holds interior rows only): the unrolled rows of a
+    // group form ONE basic block, so that ptxas can interleave their dependency chains
+    auto do_row_flat = [&](int i) {
+        const double k0 = fma(uC, a0x, vC * a0y), k1 = fma(aC, a1x, bC * a1y);
+        const double lu = fma(-2.0, uC, uS + uN), mu = fma(-2.0, uC, uE + uW);
+        const double la = fma(-2.0, aC, aS + aN), ma = fma(-2.0, aC, aE + aW);
+        const double lv = fma(-2.0, vC, vS + vN), mv = fma(-2.0, vC, vE + vW);
+        const double lb = fma(-2.0, bC, bS + bN), mb = fma(-2.0, bC, bE + bW);
+        const double ruc = fma(-c1y, ma, fma(-c1x, la, fma(c0y, mu, fma(c0x, lu, fma(k1, aS - aN, fma(-k0, uS - uN, uC))))));
+        const double rvc = fma(-c1y, mb, fma(-c1x, lb, fma(c0y, mv, fma(c0x, lv, fma(k1, bS - bN, fma(-k0, vS - vN, vC))))));
+        const double ru = jin ? ruc : uC, rv = jin ? rvc : vC;
+        un[(size_t)i * NY + j] = ru;
+        vn[(size_t)i * NY + j] = rv;
+        const double rv_w = __shfl_up_sync(0xffffffffu, rv, 1);
+        const bool wrap = li == C::BRc - 1;
+        li = wrap ? 0 : li + 1;
+        bi += wrap;
+        if (wrap) tsor = s_tid[bi * C::NBCc + bj];
+        const double c = cc * (cu * (ru - ru_prev) + cv * (rv - rv_w));
+        const int q = s_ord[li * C::BCc + lj];
+        if (jin && lane > 0) img[((size_t)(q >> 1) * NT_SOR + tsor) * 2 + (q & 1)] = c;
+        ru_prev = ru;
+    };
+#endif
     const int jw = j > 0 ? j - 1 : j, je = j < NY - 1 ? j + 1 : j;
     NNS_FINE(NNS_PROF_ADD(16, tp0); tp0 = NNS_PROF_T();)
-    for (int g = 0; g < NGROUPS; ++g) {
+    auto do_group = [&](int g, auto flat) {
         NNS_FINE(const long long tw0 = NNS_PROF_T();)
         ring.wait_full(g);
         NNS_FINE(if (a.prof) twait += clock64() - tw0;)
@@ -370,6 +424,10 @@ __device__ void stencil_pass1(const StreamArgs &a, Ring<C::NY, NGR, GR> &ring, c
                 uE = ring.row(g, 0, r)[je]; uW = ring.row(g, 0, r)[jw]; vE = ring.row(g, 1, r)[je]; vW = ring.row(g, 1, r)[jw];
                 aE = ring.row(g, 2, r)[je]; aW = ring.row(g, 2, r)[jw]; bE = ring.row(g, 3, r)[je]; bW = ring.row(g, 3, r)[jw];
             }
+#ifndef NNS_ST_BRANCHY
+            if (decltype(flat)::value) do_row_flat(i);
+            else
+#endif
             if (i >= 0) do_row(i);
         }
         // east / west of the group's last row, needed by the next step after this slot is refilled
@@ -382,7 +440,13 @@ __device__ void stencil_pass1(const StreamArgs &a, Ring<C::NY, NGR, GR> &ring, c
             NNS_FINE(if (a.prof && ts == 0) a.prof[(size_t)blockIdx.x * NPROF + 6] += clock64() - ti0;)
             if (g + NGR + 2 < NGROUPS) ring.template prefetch_l2<4>(g + NGR + 2, src, ts);
         }
-    }
+    };
+#ifndef NNS_ST_BRANCHY
+    do_group(0, std::false_type{});
+    for (int g = 1; g < NGROUPS; ++g) do_group(g, std::true_type{});
+#else
+    for (int g = 0; g < NGROUPS; ++g) do_group(g, std::false_type{});
+#endif
     uN = uC; vN = vC; uC = uS; vC = vS;                    // last row (an edge: copied)
     do_row(NX - 1);
     ring.g0 += NGROUPS;
@@ -504,6 +568,7 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
     __shared__ int s_need;
     __shared__ __align__(8) uint64_t s_full[NG], s_empty[NG];
     __shared__ short s_ord[128];          // split_ord of cell li * BC + lj (copy of c_ord: per-lane indices)
+    __shared__ __align__(8) uint64_t s_pfull;      // SOR role: the member's p has landed in the (idle) C' region
 
     double2 *Cs = reinterpret_cast<double2 *>(smem_raw);
     double *H = reinterpret_cast<double *>(smem_raw + C::CS_BYTES);
@@ -518,6 +583,7 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
 
     if (tid == 0) {
         for (int r = 0; r < NG; ++r) { mbar_init(&s_full[r], 1); mbar_init(&s_empty[r], NT_ST / 32); }
+        mbar_init(&s_pfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_mask[0] = 0ull; s_mask[1] = 0ull;
     }
@@ -589,17 +655,36 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
             };
             const bool lead = tid == 0;
             long long t0 = NNS_PROF_T();
+#ifndef NNS_SOR_DIRECT_P
+            // The member's p travels global -> shared memory as ONE bulk copy into the C' region (idle between two
+            // members' sweeps) and from there into the register blocks: a thread's block is 9 rows x 56 bytes, so the
+            // direct loads are one 32-byte sector per lane and instruction (63 x 256 sectors, ~16 k cycles per member).
+            static_assert(sizeof(double) * (size_t)NX * NY <= C::CS_BYTES, "p must fit the C' region");
+            const double *ps = reinterpret_cast<const double *>(Cs);
+            if (tid == 0 && kk == 0) {             // (later members: issued behind the previous member's store, below)
+                fence_proxy_async();               // earlier generic accesses of the region before the async-proxy write
+                mbar_expect_tx(&s_pfull, (uint32_t)(sizeof(double) * N));
+                bulk_g2s(Cs, pg, (uint32_t)(sizeof(double) * N), &s_pfull);
+            }
+            mbar_wait(&s_pfull, 0);                // phases of s_pfull alternate: p (parity 0), C' image (parity 1)
+#pragma unroll
+            for (int li = 0; li < BR; ++li)
+#pragma unroll
+                for (int lj = 0; lj < BC; ++lj) P[li][lj] = owner ? ps[(r0 + li) * NY + c0 + lj] : 0.0;
+#else
+            const double *ps = pg;
             load_block();                          // p is not touched by the stencil role before SOR finishes
+#endif
             if (owner) {                           // frozen boundary values into the unread own slots
 #pragma unroll
                 for (int lj = 0; lj < BC; ++lj) {
-                    if (!h.pubT) h.Hme[lj * NT_SOR] = pg[(size_t)(r0 - 1) * NY + c0 + lj];
-                    if (!h.pubB) h.Hme[(BC + lj) * NT_SOR] = pg[(size_t)(r0 + BR) * NY + c0 + lj];
+                    if (!h.pubT) h.Hme[lj * NT_SOR] = ps[(size_t)(r0 - 1) * NY + c0 + lj];
+                    if (!h.pubB) h.Hme[(BC + lj) * NT_SOR] = ps[(size_t)(r0 + BR) * NY + c0 + lj];
                 }
 #pragma unroll
                 for (int li = 0; li < BR; ++li) {
-                    if (!h.pubL) h.Hme[(2 * BC + li) * NT_SOR] = pg[(size_t)(r0 + li) * NY + c0 - 1];
-                    if (!h.pubR) h.Hme[(2 * BC + BR + li) * NT_SOR] = pg[(size_t)(r0 + li) * NY + c0 + BC];
+                    if (!h.pubL) h.Hme[(2 * BC + li) * NT_SOR] = ps[(size_t)(r0 + li) * NY + c0 - 1];
+                    if (!h.pubR) h.Hme[(2 * BC + BR + li) * NT_SOR] = ps[(size_t)(r0 + li) * NY + c0 + BC];
                 }
             }
             NNS_PROF_ADD(0, t0);
@@ -607,6 +692,15 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
             named_sync(BAR_READY + (kk & 1), NT_SOR + NT_ST);            // C' image of member kk is complete
             NNS_PROF_ADD(1, t0);
             t0 = NNS_PROF_T();
+#ifndef NNS_SOR_DIRECT_P
+            // the image has the layout of the C' region: one bulk copy (every SOR thread has left the region: BAR_READY)
+            if (tid == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(&s_pfull, (uint32_t)C::CS_BYTES);
+                bulk_g2s(Cs, img, (uint32_t)C::CS_BYTES, &s_pfull);
+            }
+            mbar_wait(&s_pfull, 1);
+#else
             {
                 const double2 *gi = reinterpret_cast<const double2 *>(img) + tid;
 #pragma unroll
@@ -614,6 +708,7 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
                 cp_async_wait_all();
             }
             named_sync(BAR_SOR, NT_SOR);
+#endif
             if (kk + 1 < nmine) named_arrive(BAR_CONSUMED + (kk & 1), NT_SOR + NT_ST);
             NNS_PROF_ADD(2, t0);
             t0 = NNS_PROF_T();
@@ -647,7 +742,8 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
                 };
                 unsigned long long mask = 0ull, amb = 0ull;
                 wavefront<BR, BC, RS, 1>(P, Cme, h, owner, ds.bd, tmax, cap, k, tolbits, mask, amb,
-                                     a.prof && (tid == 0 || tid == 128) ? a.prof + (size_t)blockIdx.x * NPROF + 12 + (tid >> 6) : nullptr);
+                                     a.prof && (tid == 0 || tid == 128) ? a.prof + (size_t)blockIdx.x * NPROF + 12 + (tid >> 6) : nullptr,
+                                     a.trace && blockIdx.x == 0 && kk == 1 ? a.trace + (size_t)(tid >> 5) * TRACE_STAGES * 4 : nullptr);
                 NNS_PROF_ADD(3, t0);
                 t0 = NNS_PROF_T();
                 need = sweeps_needed(mask, amb);
@@ -670,6 +766,35 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
                                          d0, d1);
                 }
             }
+#ifndef NNS_SOR_DIRECT_P
+            NNS_PROF_ADD(4, t0);
+            t0 = NNS_PROF_T();
+            {
+                // blocks -> image of rows 1 .. NX-2 in the C' region (dead after the sweeps) -> ONE bulk copy to global.
+                // The image rows are whole rows: the frozen columns 0 and NY-1 come from the boundary blocks' own slots.
+                double *pw = reinterpret_cast<double *>(Cs);
+                if (owner) {
+#pragma unroll
+                    for (int li = 0; li < BR; ++li) {
+#pragma unroll
+                        for (int lj = 0; lj < BC; ++lj) pw[(r0 + li) * NY + c0 + lj] = P[li][lj];
+                        if (!h.pubL) pw[(r0 + li) * NY + c0 - 1] = h.Hme[(2 * BC + li) * NT_SOR];
+                        if (!h.pubR) pw[(r0 + li) * NY + c0 + BC] = h.Hme[(2 * BC + BR + li) * NT_SOR];
+                    }
+                }
+                fence_proxy_async();               // generic-proxy writes before the async-proxy read of the bulk copy
+                named_sync(BAR_SOR, NT_SOR);
+                if (tid == 0) {
+                    bulk_s2g(pg + NY, pw + NY, (uint32_t)(sizeof(double) * (NX - 2) * NY));
+                    asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory");
+                    if (kk + 1 < nmine) {          // the region is free again: the next member's p is already on its way
+                        mbar_expect_tx(&s_pfull, (uint32_t)(sizeof(double) * N));
+                        bulk_g2s(Cs, a.p + (size_t)member(kk + 1) * N, (uint32_t)(sizeof(double) * N), &s_pfull);
+                    }
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // complete (not only read): the stencil role re-reads p after BAR_DONE
+                }
+            }
+#else
             if (owner) {
 #pragma unroll
                 for (int li = 0; li < BR; ++li)
@@ -678,6 +803,7 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
             }
             NNS_PROF_ADD(4, t0);
             t0 = NNS_PROF_T();
+#endif
             if (a.sweeps && tid == 0) a.sweeps[m] = need;
             __threadfence();              // p is re-read by the stencil role, partly through the TMA unit
             named_arrive(BAR_DONE + (kk & 1), NT_SOR + NT_ST);
@@ -1055,7 +1181,14 @@ static void build_tables(StreamPlan &pl) {
     for (const Item &it : items) n_even += !(it.key & 1);
     std::vector<int> tid_of((size_t)NB), thr((size_t)NB);
     for (int t = 0; t < NB; ++t) {
+#ifndef NNS_SOR_SAME_PAIR
+        // the warps of the odd class in reverse order: an SM sub-partition (warp % 4) then hosts an early-diagonal warp of
+        // one class and a late-diagonal warp of the other, so that during the fill / drain stages of the wavefront the
+        // active warps sit on different sub-partitions instead of sharing one
+        thr[t] = t < n_even ? t : NT_SOR / 2 + 32 * (NW_SOR / 2 - 1 - (t - n_even) / 32) + (t - n_even) % 32;
+#else
         thr[t] = t < n_even ? t : NT_SOR / 2 + (t - n_even);
+#endif
         tid_of[(size_t)items[t].bi * NBC + items[t].bj] = thr[t];
     }
     pl.desc.assign(NT_SOR, SBlock{0, 0, -1, -1, -1, -1, 0, 0});     // r0 == 0 marks a thread without a block
@@ -1095,7 +1228,25 @@ static void build_tables(StreamPlan &pl) {
 // Debug aid: print and reset the phase counters (NNS_STREAM_PROF=1), averaged over CTAs.
 void chorin_stream_prof_dump(nns_handle *h) {
     StreamPlan *pl = static_cast<StreamPlan *>(h->stream_plan);
-    if (pl && pl->d_trace) {
+#ifdef NNS_STREAM_TRACE
+    if (pl && pl->d_trace && !pl->wave) {
+        std::vector<long long> t((size_t)NW_SOR * TRACE_STAGES * 4);
+        cudaDeviceSynchronize();
+        cudaMemcpy(t.data(), pl->d_trace, sizeof(long long) * t.size(), cudaMemcpyDeviceToHost);
+        // per stage and warp: start (after the previous release) relative to warp 0, cycles start -> arrival, arrival -> release, active lanes
+        for (int st = 0; st < TRACE_STAGES; ++st) {
+            if (!t[(size_t)st * 4]) continue;
+            fprintf(stderr, "[nns stream trace] T %3d len %5lld:", st, st + 1 < TRACE_STAGES && t[(size_t)(st + 1) * 4] ? t[(size_t)(st + 1) * 4] - t[(size_t)st * 4] : 0ll);
+            for (int w = 0; w < NW_SOR; ++w) {
+                const long long *e = &t[((size_t)w * TRACE_STAGES + st) * 4];
+                fprintf(stderr, " | %2lld %4lld+%4lld", e[2], e[1] - e[0], e[3] - e[1]);
+            }
+            fprintf(stderr, "\n");
+        }
+        cudaMemset(pl->d_trace, 0, sizeof(long long) * t.size());
+    }
+#endif
+    if (pl && pl->d_trace && pl->wave) {
         std::vector<long long> t((size_t)NW_SOR * 16 * 4);
         cudaDeviceSynchronize();
         cudaMemcpy(t.data(), pl->d_trace, sizeof(long long) * t.size(), cudaMemcpyDeviceToHost);
@@ -1177,6 +1328,12 @@ int chorin_stream_step(nns_handle *h, const double *uc, const double *vc, const 
         NNS_CUDA(cudaMemset(pl->d_img, 0, sizeof(double2) * C::NCH * NT_SOR * (size_t)pl->grid * N_SCRATCH));
         NNS_CUDA(cudaFuncSetAttribute(chorin_stream_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)C::SMEM_BYTES));
+#ifdef NNS_STREAM_TRACE
+        if (getenv("NNS_STREAM_TRACE")) {
+            NNS_CUDA(cudaMalloc(&pl->d_trace, sizeof(long long) * NW_SOR * TRACE_STAGES * 4));
+            NNS_CUDA(cudaMemset(pl->d_trace, 0, sizeof(long long) * NW_SOR * TRACE_STAGES * 4));
+        }
+#endif
 #ifdef NNS_ENABLE_WAVE
         const char *mode = getenv("NNS_STREAM_MODE");
         pl->wave = mode && strcmp(mode, "wave") == 0 && h->g.nit - 1 <= 64;

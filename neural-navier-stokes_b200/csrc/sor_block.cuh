@@ -84,6 +84,22 @@ __host__ __device__ constexpr int split_ord(int li, int lj) {
 // TRACK: 0 none; 1 fast: running maximum of the high words of |p' - p| on the integer pipe (decides
 // "max|dp| <= tol" unless the maximum shares its high word with tol: ambiguous, resolved by an exact
 // re-run); 2 exact 64-bit comparison per cell.
+// Running maximum of the high words of |d| for the fast exit test.  The high word of a non-negative double orders like
+// the same bits read as a float, so the maximum runs on the FP32 pipe (FMNMX with the |x| operand modifier); the
+// integer form (LOP3 + VIMNMX3) issues on a slow pipe on B200 (scripts/micro/pipe_bench.cu: a third of the step).
+// max.NaN keeps a high word >= 0x7f800001 (|d| >= 2^1017, inf or NaN: a float NaN pattern) as a NaN, which compares
+// above every tolerance as an unsigned integer -- "violated", as the exact test says.  Denormal patterns are kept
+// (the library is built without -ftz).
+__device__ __forceinline__ unsigned track_hi(unsigned m, double d) {
+#ifdef NNS_TRACK_INT
+    return max(m, (unsigned)__double2hiint(d) & 0x7fffffffu);
+#else
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(__uint_as_float(m)), "f"(fabsf(__int_as_float(__double2hiint(d)))));
+    return __float_as_uint(r);
+#endif
+}
+
 template <int BR, int BC, int RS, int R0, int R1, int TRACK>
 __device__ __forceinline__ void block_sweep(double (&P)[BR][BC], const double2 *__restrict__ Cme, const SHalo<BR, BC> &h,
                                             const Coef &k, unsigned long long tolbits, unsigned &mhi, bool &viol) {
@@ -135,13 +151,13 @@ __device__ __forceinline__ void block_sweep(double (&P)[BR][BC], const double2 *
                 const double pn = fma(k.ca, n, fma(k.cb, w, base[kd & 1][r]));
                 if (TRACK) {
                     const double d = pn - P[li][lj];
-                    if (TRACK == 1) mhi = max(mhi, (unsigned)__double2hiint(d) & 0x7fffffffu);
+                    if (TRACK == 1) mhi = track_hi(mhi, d);
                     else viol |= exceeds_bits(d, tolbits);
                 }
                 P[li][lj] = pn;
 #else                       // d in 5 DFMAs, p += d in place (no register renaming at the loop back-edge)
                 const double d = fma(k.ca, n, fma(k.cb, w, base[kd & 1][r]));
-                if (TRACK == 1) mhi = max(mhi, (unsigned)__double2hiint(d) & 0x7fffffffu);
+                if (TRACK == 1) mhi = track_hi(mhi, d);
                 if (TRACK == 2) viol |= exceeds_bits(d, tolbits);
                 P[li][lj] += d;
 #endif
@@ -223,7 +239,7 @@ __device__ __forceinline__ void block_sweep_pf(double (&P)[BR][BC], const double
                 const double n = li > 0 ? P[li - 1][lj] : h.hN[lj * NT_SOR];
                 const double w = lj > 0 ? P[li][lj - 1] : h.hW[li * NT_SOR];
                 const double d = fma(k.ca, n, fma(k.cb, w, base[kd & 1][r]));
-                if (TRACK == 1) mhi = max(mhi, (unsigned)__double2hiint(d) & 0x7fffffffu);
+                if (TRACK == 1) mhi = track_hi(mhi, d);
                 if (TRACK == 2) viol |= exceeds_bits(d, tolbits);
                 P[li][lj] += d;
             }
@@ -318,7 +334,7 @@ __device__ __forceinline__ void block_sweep_tm(double (&P)[BR][BC], uint32_t tmc
                 const double n = li > 0 ? P[li - 1][lj] : h.hN[lj * NT_SOR];
                 const double w = lj > 0 ? P[li][lj - 1] : h.hW[li * NT_SOR];
                 const double d = fma(k.ca, n, fma(k.cb, w, base[kd & 1][r]));
-                mhi = max(mhi, (unsigned)__double2hiint(d) & 0x7fffffffu);
+                mhi = track_hi(mhi, d);
                 // p += d for the lanes inside the band, p unchanged (+ 0 * d) for the others: one DFMA, like the
                 // DADD of the legacy sweep and bit-identical to it for actf == 1 (a select would cost two extra
                 // instructions per cell)

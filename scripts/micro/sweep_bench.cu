@@ -7,7 +7,10 @@
 using namespace nns;
 
 template <int TRACK, int R0, int R1>
-__global__ void __launch_bounds__(256, 1) bench(double *out, long long *cyc, int iters, int nsweep_warps, int noise_warps) {
+#ifndef MAXR
+#define MAXR 255
+#endif
+__global__ void __maxnreg__(MAXR) bench(double *out, long long *cyc, int iters, int nsweep_warps, int noise_warps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2 *Cs = reinterpret_cast<double2 *>(smem_raw);
     double *H = reinterpret_cast<double *>(smem_raw + sizeof(double2) * 32 * NT_SOR);
@@ -62,6 +65,58 @@ static void run(double *out, long long *cyc, size_t smem, int nw, int noise) {
            (R1 - R0) * 7, nw, noise, mx / iters, mx / iters / ((R1 - R0) * 7) / ((nw + 3) / 4));
 }
 
+template <int TRACK, bool BARRIER>
+__global__ void __maxnreg__(MAXR) bench_lockstep(double *out, long long *cyc, int iters) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *Cs = reinterpret_cast<double2 *>(smem_raw);
+    double *H = reinterpret_cast<double *>(smem_raw + sizeof(double2) * 32 * NT_SOR);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int q = tid; q < 32 * NT_SOR; q += blockDim.x) { Cs[q] = make_double2(1e-3 * q, 2e-3 * q); H[q] = 1e-4 * q; }
+    __syncthreads();
+    double P[9][7];
+#pragma unroll
+    for (int li = 0; li < 9; ++li)
+#pragma unroll
+        for (int lj = 0; lj < 7; ++lj) P[li][lj] = 0.01 * (li + lj) + tid;
+    SHalo<9, 7> h;
+    h.Hme = H + tid; h.pubT = h.pubB = h.pubL = h.pubR = true;
+    h.hN = H + 7 * NT_SOR + ((tid + 1) & 255); h.hS = H + ((tid + 2) & 255);
+    h.hW = H + 23 * NT_SOR + ((tid + 3) & 255); h.hE = H + 14 * NT_SOR + ((tid + 4) & 255);
+    Coef k; k.ca = 0.3125; k.cb = 0.3125; k.cc = -1.25; k.beta = 1.25; k.tol = 5e-6;
+    unsigned mhi = 0; bool v = false;
+    const int par = warp >> 2;
+    long long tin = 0;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+        const long long a0 = clock64();
+        if (!((it + par) & 1)) block_sweep<9, 7, 5, 0, 5, TRACK>(P, Cs + tid, h, k, 0x3ed4f8b588e368f1ull, mhi, v);
+        else block_sweep<9, 7, 5, 5, 9, TRACK>(P, Cs + tid, h, k, 0x3ed4f8b588e368f1ull, mhi, v);
+        tin += clock64() - a0;
+        if (BARRIER) asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    const long long t1 = clock64();
+    if ((tid & 31) == 0) { cyc[blockIdx.x * 16 + warp] = t1 - t0; cyc[blockIdx.x * 16 + 8 + warp] = tin; }
+    double s = mhi + v;
+#pragma unroll
+    for (int li = 0; li < 9; ++li)
+#pragma unroll
+        for (int lj = 0; lj < 7; ++lj) s += P[li][lj];
+    if (s == 1.2345) out[0] = s;
+}
+
+template <int TRACK, bool BARRIER>
+static void run_lockstep(double *out, long long *cyc, size_t smem) {
+    const int iters = 2000;
+    long long h[16];
+    cudaFuncSetAttribute(bench_lockstep<TRACK, BARRIER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    bench_lockstep<TRACK, BARRIER><<<148, 256, smem>>>(out, cyc, iters);
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("lockstep top/bottom alternating, 8 warps, barrier %d: %.0f cycles per stage, %.0f inside block_sweep (warp 0), %.0f (warp 4)\n",
+           (int)BARRIER, (double)h[0] / iters, (double)h[8] / iters, (double)h[12] / iters);
+}
+
 int main() {
     double *out; long long *cyc;
     cudaMalloc(&out, 64); cudaMalloc(&cyc, sizeof(long long) * 16 * 148);
@@ -75,6 +130,8 @@ int main() {
     }
     run<1, 0, 9>(out, cyc, smem, 4, 4);
     run<1, 0, 5>(out, cyc, smem, 4, 4);
+    run_lockstep<1, false>(out, cyc, smem);
+    run_lockstep<1, true>(out, cyc, smem);
     printf("last error: %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
