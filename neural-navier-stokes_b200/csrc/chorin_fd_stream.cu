@@ -79,6 +79,7 @@ struct StreamArgs {
     int *redo_list;          // members whose SOR loop stops early (or undecided by the fast test): re-run pass
     int *redo_count;
     double *pscr;            // [gridDim.x][2][NX*NY] SOR results before p_bc (L2-resident scratch)
+    unsigned depmask[NW_SOR];            // per SOR warp: the warps that hold neighbours of its blocks (stage hand-off)
     int wamin[NW_SOR], wrange[NW_SOR];   // per SOR warp: first block diagonal and spread of its lanes
     int rmax;                // largest spread
     long long *trace;        // optional (NNS_WAVE_TRACE=1): clock64 of CTA 0 per SOR warp at sweep start / barrier arrival / release
@@ -128,6 +129,23 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(b))
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_release(uint64_t *b) {      // SASS: a bare SYNCS.ARRIVE (no MEMBAR)
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+// blocking wait with a hardware suspend hint: the waiting warp sleeps instead of polling through the LSU
+__device__ __forceinline__ void mbar_wait_acquire(uint64_t *b, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP_A:\n"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 P1, [%0], %1, 0x989680;\n"
+        "@P1 bra WAIT_DONE_A;\n"
+        "bra WAIT_LOOP_A;\n"
+        "WAIT_DONE_A:\n"
+        "}\n" ::"r"(smem_u32(b)),
+        "r"(parity)
+        : "memory");
+}
 // 1-D bulk copy shared -> global (bulk async-group completion)
 __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
@@ -155,8 +173,20 @@ __constant__ short c_ord[128];     // diag_ord of cell q = li * BC + lj (host-fi
 template <int BR, int BC, int RS, int TRACK>
 __device__ __forceinline__ void wavefront(double (&P)[BR][BC], const double2 *Cme, const SHalo<BR, BC> &h, bool owner,
                                           int sd, int tmax, int cap, const Coef &k, unsigned long long tolbits,
-                                          unsigned long long &mask, unsigned long long &amb, long long *prof = nullptr,
-                                          long long *trace = nullptr) {
+                                          unsigned long long &mask, unsigned long long &amb, uint64_t (*hb)[2], unsigned dep, int &gbase,
+                                          long long *prof = nullptr, long long *trace = nullptr) {
+    // One CTA-wide (SOR role) barrier per stage.  EXPERIMENT (-DNNS_SOR_STAGE_HANDOFF, measured slower: 3.94 against 3.62
+    // ms/step): point-to-point hand-off instead.  A sub-block sweep of stage T reads what its four neighbours published
+    // in stage T-1 and overwrites what they read in stage T-1, so a warp may enter stage T as soon as the warps that hold
+    // neighbours of its blocks (bit mask `dep`, host-built, symmetric) have completed T-1.  Every warp owns two mbarriers
+    // (stages of even / odd global index G, arrival count = number of its neighbour warps): after stage G a warp arrives
+    // (release: a bare SYNCS.ARRIVE) on hb[c][G & 1] of each neighbour warp c, before stage G it waits (acquire,
+    // hardware-suspended) for phase (G-1)/2 of its own hb[w][(G-1) & 1]; a neighbour cannot complete G+1 -- the next
+    // arrival on the same barrier -- before this warp has completed G, so a barrier is never more than one phase ahead
+    // of its waiter.  Bit-identical results, but every warp has 5 of the 7 others as neighbours: it is a CTA barrier
+    // built from slower parts (~270 cycles of wait per stage in the trace against ~130 for BAR.SYNC).  Polling progress
+    // counters through the LSU instead of mbarriers: 7.6 ms/step (the pollers starve the warps they wait for).
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (owner) publish<BR, BC, 0, BR>(P, h);   // the whole perimeter once
     named_sync(BAR_SOR, NT_SOR);
     const unsigned tolhi = (unsigned)(tolbits >> 32);
@@ -167,6 +197,13 @@ __device__ __forceinline__ void wavefront(double (&P)[BR][BC], const double2 *Cm
     for (int T = 0; T <= tmax; ++T) {
         const int q = T - sd;                       // 2s for the top sub-block, 2s + 1 for the bottom one
         const bool work = owner && q >= 0 && q <= 2 * (cap - 1) + 1;
+#ifdef NNS_SOR_STAGE_HANDOFF
+#ifdef NNS_STREAM_TRACE
+        if (trace && lane == 0 && T < TRACE_STAGES) trace[T * 4 + 3] = clock64();
+#endif
+        const int G = gbase + T;
+        if (G > 0) mbar_wait_acquire(&hb[wid][(G - 1) & 1], (unsigned)((G - 1) >> 1) & 1u);
+#endif
 #ifdef NNS_STREAM_TRACE
         const unsigned nact = __popc(__ballot_sync(0xffffffffu, work));
         if (trace && (threadIdx.x & 31) == 0 && T < TRACE_STAGES) { trace[T * 4 + 0] = clock64(); trace[T * 4 + 2] = nact; }
@@ -198,11 +235,20 @@ __device__ __forceinline__ void wavefront(double (&P)[BR][BC], const double2 *Cm
         __syncwarp();
         if (trace && (threadIdx.x & 31) == 0 && T < TRACE_STAGES) trace[T * 4 + 1] = clock64();
 #endif
+#ifndef NNS_SOR_STAGE_HANDOFF
         named_sync(BAR_SOR, NT_SOR);
 #ifdef NNS_STREAM_TRACE
         if (trace && (threadIdx.x & 31) == 0 && T < TRACE_STAGES) trace[T * 4 + 3] = clock64();
 #endif
+#else
+        __syncwarp();
+        if (lane < NW_SOR && ((dep >> lane) & 1u)) mbar_arrive_release(&hb[lane][G & 1]);
+#endif
     }
+#ifdef NNS_SOR_STAGE_HANDOFF
+    gbase += tmax + 1;
+    named_sync(BAR_SOR, NT_SOR);
+#endif
 }
 
 // Sequential BC list on a row-major GLOBAL field by the 128 stencil threads (boundary.py:34-86).
@@ -568,6 +614,7 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
     __shared__ int s_need;
     __shared__ __align__(8) uint64_t s_full[NG], s_empty[NG];
     __shared__ short s_ord[128];          // split_ord of cell li * BC + lj (copy of c_ord: per-lane indices)
+    __shared__ __align__(8) uint64_t s_hb[NW_SOR][2];   // SOR role: stage hand-off barriers (wavefront())
     __shared__ __align__(8) uint64_t s_pfull;      // SOR role: the member's p has landed in the (idle) C' region
 
     double2 *Cs = reinterpret_cast<double2 *>(smem_raw);
@@ -584,6 +631,7 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
     if (tid == 0) {
         for (int r = 0; r < NG; ++r) { mbar_init(&s_full[r], 1); mbar_init(&s_empty[r], NT_ST / 32); }
         mbar_init(&s_pfull, 1);
+        for (int w = 0; w < NW_SOR; ++w) { mbar_init(&s_hb[w][0], __popc(a.depmask[w])); mbar_init(&s_hb[w][1], __popc(a.depmask[w])); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_mask[0] = 0ull; s_mask[1] = 0ull;
     }
@@ -643,6 +691,7 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
         const int cap = a.g.nit - 1;
         const int tmax = 2 * C::NBRc + C::NBCc - 2 + 2 * (cap - 1);      // last sub-block diagonal + 2 (cap - 1)
 
+        int gbase = 0;                     // global stage index of the hand-off barriers (wavefront())
         for (int kk = 0; kk < nmine; ++kk) {
             const int m = member(kk);
             double *pg = a.p + (size_t)m * N;
@@ -741,7 +790,7 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
                     return s_need;
                 };
                 unsigned long long mask = 0ull, amb = 0ull;
-                wavefront<BR, BC, RS, 1>(P, Cme, h, owner, ds.bd, tmax, cap, k, tolbits, mask, amb,
+                wavefront<BR, BC, RS, 1>(P, Cme, h, owner, ds.bd, tmax, cap, k, tolbits, mask, amb, s_hb, a.depmask[tid >> 5], gbase,
                                      a.prof && (tid == 0 || tid == 128) ? a.prof + (size_t)blockIdx.x * NPROF + 12 + (tid >> 6) : nullptr,
                                      a.trace && blockIdx.x == 0 && kk == 1 ? a.trace + (size_t)(tid >> 5) * TRACE_STAGES * 4 : nullptr);
                 NNS_PROF_ADD(3, t0);
@@ -754,7 +803,7 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
                     // max|dp| of the deciding sweep shares its high word with tol: repeat with the exact test
                     load_block();
                     mask = 0ull; amb = 0ull;
-                    wavefront<BR, BC, RS, 2>(P, Cme, h, owner, ds.bd, tmax, cap, k, tolbits, mask, amb);
+                    wavefront<BR, BC, RS, 2>(P, Cme, h, owner, ds.bd, tmax, cap, k, tolbits, mask, amb, s_hb, a.depmask[tid >> 5], gbase);
                     need = sweeps_needed(mask, 0ull);
                 }
                 if (need < cap) {
@@ -763,7 +812,7 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
                     load_block();
                     unsigned long long d0 = 0ull, d1 = 0ull;
                     wavefront<BR, BC, RS, 0>(P, Cme, h, owner, ds.bd, 2 * C::NBRc + C::NBCc - 2 + 2 * (need - 1), need, k, tolbits,
-                                         d0, d1);
+                                         d0, d1, s_hb, a.depmask[tid >> 5], gbase);
                 }
             }
 #ifndef NNS_SOR_DIRECT_P
@@ -1155,6 +1204,7 @@ struct StreamPlan {
     long long *d_trace = nullptr;
     double *d_pscr = nullptr;   // wave kernel: [grid][2][NX*NY] SOR results
     int *d_redo = nullptr;      // wave kernel: [1 + batch] counter, member list of the re-run pass
+    unsigned depmask[NW_SOR] = {0};
     int wamin[NW_SOR] = {0}, wrange[NW_SOR] = {0}, rmax = 0;
     int grid = 0;
     bool ok = false;
@@ -1208,6 +1258,14 @@ static void build_tables(StreamPlan &pl) {
         d.bd = (short)(2 * bi + bj);
         d.pad = 0;
         pl.desc[t] = d;
+    }
+    // stage hand-off: warp w waits for the warps that hold a neighbour of one of its blocks
+    for (int w = 0; w < NW_SOR; ++w) pl.depmask[w] = 0u;
+    for (int t = 0; t < NT_SOR; ++t) {
+        const SBlock &d = pl.desc[t];
+        if (d.r0 <= 0) continue;
+        for (short nb : {d.nN, d.nS, d.nW, d.nE})
+            if (nb >= 0 && (nb >> 5) != (t >> 5)) pl.depmask[t >> 5] |= 1u << (nb >> 5);
     }
     // wave kernel: first block diagonal and spread of every SOR warp (members change per warp)
     pl.rmax = 0;
@@ -1371,6 +1429,7 @@ int chorin_stream_step(nns_handle *h, const double *uc, const double *vc, const 
     a.nonfinite = h->d_nonfinite;
     a.prof = pl->d_prof;
     a.trace = pl->d_trace;
+    for (int w = 0; w < NW_SOR; ++w) a.depmask[w] = pl->depmask[w];
     const int grid = count < pl->grid ? count : pl->grid;
 #ifdef NNS_ENABLE_WAVE
     if (pl->wave) {
