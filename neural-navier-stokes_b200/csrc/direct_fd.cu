@@ -169,28 +169,6 @@ __global__ void __launch_bounds__(1024, 1) direct_chip_kernel(const DirectArgs a
 // ---- cluster path -----------------------------------------------------------------------
 // Rows [i0, i1) of the member belong to this CTA; shared-memory row index li = i - i0 + 1 (li = 0 and li = nloc + 1
 // are the halo rows owned by the neighbouring CTAs).  smem: P0, P1, Bs of (band + 2) * pitch doubles each.
-__device__ __forceinline__ void band_apply_bc_smem(double *A, int nx, int ny, int pitch, int i0, int i1, const BcList &L,
-                                                   const double *bcval, double dx, double dy) {
-    const int nloc = i1 - i0;
-    for (int k = 0; k < L.n; ++k) {
-        const double g = bcval ? bcval[L.slot[k]] : L.value[k];
-        const int side = L.side[k];
-        const bool neu = L.type[k] == NNS_BC_NEUMANN;
-        if (side == NNS_SIDE_LEFT) {
-            if (i0 == 0)
-                for (int j = threadIdx.x; j < ny; j += blockDim.x) A[1 * pitch + j] = neu ? A[2 * pitch + j] - dx * g : g;
-        } else if (side == NNS_SIDE_RIGHT) {
-            if (i1 == nx)
-                for (int j = threadIdx.x; j < ny; j += blockDim.x) A[nloc * pitch + j] = neu ? A[(nloc - 1) * pitch + j] + dx * g : g;
-        } else {
-            const int j = side == NNS_SIDE_BOTTOM ? 0 : ny - 1, jn = side == NNS_SIDE_BOTTOM ? 1 : ny - 2;
-            const double sg = side == NNS_SIDE_BOTTOM ? -dy : dy;
-            for (int li = 1 + threadIdx.x; li <= nloc; li += blockDim.x) A[li * pitch + j] = neu ? A[li * pitch + jn] + sg * g : g;
-        }
-        __syncthreads();
-    }
-}
-
 __device__ __forceinline__ void band_apply_bc_global(double *A, int nx, int ny, int i0, int i1, const BcList &L,
                                                      const double *bcval, double dx, double dy) {
     for (int k = 0; k < L.n; ++k) {
@@ -214,13 +192,25 @@ __device__ __forceinline__ void band_apply_bc_global(double *A, int nx, int ny, 
 }
 
 // Point-to-point hand-off between neighbouring CTAs of the cluster: the producer's threads store the band edge into the
-// consumer's shared memory, thread 0 then arrives (release, cluster scope) on the consumer's mbarrier; the consumer's
-// threads wait on their own mbarrier (acquire, cluster scope).  A full cluster barrier per sweep costs several times more.
+// consumer's shared memory with st.async, which completes on the consumer's mbarrier; the consumer's warps wait on their
+// own mbarrier.  A full cluster barrier per sweep costs several times more.
 __device__ __forceinline__ uint32_t dsm_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void remote_arrive(const void *local_bar, unsigned rank) {
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, unsigned rank) {
     uint32_t ra;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(dsm_u32(local_bar)), "r"(rank));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local), "r"(rank));
+    return ra;
+}
+// Asynchronous store into a neighbouring CTA's shared memory that completes (transaction bytes) on an mbarrier of that
+// CTA: the consumer that sees the phase complete sees the data -- no fence on either side.  (A release arrive or a fence at
+// cluster scope compiles to MEMBAR.ALL.GPU + CCTL.IVALL: three of those per warp and sweep were half of the sweep time.)
+__device__ __forceinline__ void st_async_f64(uint32_t raddr, double v, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(raddr), "d"(v), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void st_async_f64x2(uint32_t raddr, double v0, double v1, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(raddr), "d"(v0), "d"(v1), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void mbar_arm(const void *bar, uint32_t bytes) {      // the one expected arrival + the bytes of the next phase
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dsm_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cluster_wait(const void *bar, uint32_t parity) {
     unsigned spins = 0;
@@ -235,12 +225,42 @@ __device__ __forceinline__ void cluster_wait(const void *bar, uint32_t parity) {
     } while (!ok);
 }
 
-__global__ void __launch_bounds__(1024, 1) direct_cluster_kernel(const DirectArgs a, int band) {
-    extern __shared__ double smem[];
-    __shared__ __align__(8) unsigned long long hbar[2];       // [0]: the CTA above has delivered my upper halo row, [1]: the CTA below my lower one
+// One Jacobi sweep of the cluster path is ordered so that the exchange with the neighbouring CTAs hides behind the rest of
+// the sweep:
+//   1. wait for the neighbours' band edges of the previous sweep (my halo rows of Pc);
+//   2. ALL threads compute the two edge rows of the band, store them locally and straight into the neighbours' halo rows
+//      (distributed shared memory, st.async completing on the neighbours' mbarriers: no fence, no separate arrival);
+//   3. the interior rows of the band; CTA barrier;
+//   4. only in the two CTAs that hold a global edge row (i = 0 or nx-1): the cells of that row; CTA barrier.
+// The p BC list is applied in list order by the reference (boundary.py:34-86), but only the four corner cells of the grid
+// depend on the order: a cell of column 0 / ny-1 in another row is written by bottom / top entries only and reads the new
+// value next to it, a non-corner cell of row 0 / nx-1 is written by left / right entries only and reads the new value in
+// the adjacent row -- the LAST entry of that side decides.  So the thread of column 1 (ny-2) writes the column cells with
+// its row (the edge rows are final before they are pushed), all threads write the edge row after the sweep, and one thread
+// per corner replays the list in registers on the corner and its two neighbours (their values before the first entry are
+// the previous sweep's: Jacobi copies edge cells through).  Walking the list with a barrier (or a __syncwarp) per entry
+// cost 1600-1900 cycles per sweep in the two edge CTAs, which set the pace of the whole cluster.
+// Two mbarriers per neighbour, alternating with the sweep parity (arrival count 1 = the owner's re-arm with the expected
+// bytes of a halo row): a neighbour's stores of sweep g+2 need my stores of g+1, which follow my wait for g, so a barrier
+// is never more than one phase ahead of its waiter.
+//
+// Row layout in shared memory (pitch even, rows 16-byte aligned): the computed columns j = JLO .. JLO+nj-1 sit at the even
+// index 2 + (j - JLO), so a thread updates a PAIR of cells with 128-bit loads of the centre / north / south / b pairs and
+// two scalar loads for the outer west / east operands (3.5 shared-memory instructions per cell instead of 7):
+//   walls   : JLO = 1, nj = ny-2; index 1 = column 0, index ny = column ny-1 (edge values)        => column j at 1 + j
+//   periodic: JLO = 0, nj = ny;   index 1 = copy of column ny-1, index ny+2 = copy of column 0    => column j at 2 + j
+template <bool PER>
+__global__ void __launch_bounds__(512, 1) direct_cluster_kernel(const DirectArgs a, int band, int pitch) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) unsigned long long hbar[2][2];    // [sweep parity][0: from the CTA above, 1: from the CTA below]
+    __shared__ double s_pval[NNS_MAX_BC];                     // values of the p BC entries of this member
+    __shared__ int s_pcode[NNS_MAX_BC];                       // side | type << 8 of the p BC entries
     cg::cluster_group cluster = cg::this_cluster();
+    constexpr int OFF = PER ? 2 : 1;
     const int NC = (int)cluster.num_blocks(), r = (int)cluster.block_rank();
-    const int nx = a.g.nx, ny = a.g.ny, pitch = ny | 1;
+    const int nx = a.g.nx, ny = a.g.ny;
+    const int nj = PER ? ny : ny - 2, xend = 2 + nj;          // computed cells of a row: indices [2, xend)
+    const uint32_t row_bytes = 8u * (uint32_t)(nj + 2);      // what a neighbour stores into one of my halo rows per sweep: indices 1 .. xend
     const size_t N = (size_t)nx * ny;
     const int b = blockIdx.x / NC, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int i0 = r * band, i1 = min(nx, i0 + band), nloc = i1 - i0;
@@ -255,24 +275,96 @@ __global__ void __launch_bounds__(1024, 1) direct_cluster_kernel(const DirectArg
     const double r2dx = 1.0 / (2.0 * dx), r2dy = 1.0 / (2.0 * dy), rdt = 1.0 / dt;
     double *ug = a.u + (size_t)b * N, *vg = a.v + (size_t)b * N, *pg = a.p + (size_t)b * N;
     double *us = a.su + (size_t)b * N, *vs = a.sv + (size_t)b * N;
-    const bool per = a.flags & NNS_FLAG_PERIODIC_X;          // periodic-x extension: the column neighbours wrap around
-    const double fdt = per ? a.force_x * dt : 0.0;
+    const double fdt = PER ? a.force_x * dt : 0.0;
 
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dsm_u32(&hbar[0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dsm_u32(&hbar[1])));
+        for (int k = 0; k < 4; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dsm_u32(&hbar[k >> 1][k & 1])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int k = 0; k < 4; ++k) mbar_arm(&hbar[k >> 1][k & 1], row_bytes);       // sweeps 0 and 1
     }
-    cluster.sync();            // every CTA's mbarriers exist before the first remote arrival
-    uint32_t hpar = 0;
+    cluster.sync();            // every CTA's mbarriers exist (and are armed) before the first remote store
     const bool has_above = r > 0, has_below = r < NC - 1;
-    // own rows and the two halo rows of p from global memory
+    const bool edge_cta = i0 == 0 || i1 == nx;
+    // my edge rows in the neighbours' halo rows: row li = 1 is the lower halo row (band + 1) of the CTA above, row nloc the
+    // upper halo row (0) of the CTA below; one pointer per buffer
+    // (shared::cluster addresses; 0 = no neighbour.  My barrier [par][1] of the CTA above counts what I, its lower
+    // neighbour, store; [par][0] of the CTA below what I, its upper neighbour, store.)
+    uint32_t remA_c = has_above ? mapa_u32(dsm_u32(Pc + (size_t)(band + 1) * pitch), r - 1) : 0u;
+    uint32_t remA_n = has_above ? mapa_u32(dsm_u32(Pn + (size_t)(band + 1) * pitch), r - 1) : 0u;
+    uint32_t remB_c = has_below ? mapa_u32(dsm_u32(Pc), r + 1) : 0u;
+    uint32_t remB_n = has_below ? mapa_u32(dsm_u32(Pn), r + 1) : 0u;
+    const uint32_t barA0 = has_above ? mapa_u32(dsm_u32(&hbar[0][1]), r - 1) : 0u, barA1 = has_above ? mapa_u32(dsm_u32(&hbar[1][1]), r - 1) : 0u;
+    const uint32_t barB0 = has_below ? mapa_u32(dsm_u32(&hbar[0][0]), r + 1) : 0u, barB1 = has_below ? mapa_u32(dsm_u32(&hbar[1][0]), r + 1) : 0u;
+    // the last bottom / top entry of the p list: 0 none, 1 Dirichlet, 2 Neumann
+    int bk = 0, tk = 0, ek = 0;
+    double bgv = 0.0, tgv = 0.0, egv = 0.0;
+    for (int k = 0; k < a.pbc.n; ++k) {
+        const double g = bcval ? bcval[a.pbc.slot[k]] : a.pbc.value[k];
+        const int kind = a.pbc.type[k] == NNS_BC_NEUMANN ? 2 : 1;
+        if (a.pbc.side[k] == NNS_SIDE_BOTTOM) { bk = kind; bgv = g; }
+        if (a.pbc.side[k] == NNS_SIDE_TOP) { tk = kind; tgv = g; }
+        if ((a.pbc.side[k] == NNS_SIDE_LEFT && i0 == 0) || (a.pbc.side[k] == NNS_SIDE_RIGHT && i1 == nx)) { ek = kind; egv = g; }
+    }
+    // the global edge row of this CTA (if any): its row, the adjacent row, the sign of the Neumann step
+    const int erow = i0 == 0 ? 1 : nloc, arow = i0 == 0 ? 2 : nloc - 1, eside = i0 == 0 ? NNS_SIDE_LEFT : NNS_SIDE_RIGHT;
+    const double esg = i0 == 0 ? -dx : dx;
+    if (tid < a.pbc.n) { s_pval[tid] = bcval ? bcval[a.pbc.slot[tid]] : a.pbc.value[tid]; s_pcode[tid] = a.pbc.side[tid] | (a.pbc.type[tid] << 8); }
+    // own rows and the two halo rows of p from global memory (both buffers: the pad / copy cells must be finite everywhere)
+    for (size_t q = tid; q < 3 * plane; q += blockDim.x) smem[q] = 0.0;
+    __syncthreads();
     for (int li = warp; li < nloc + 2; li += nwarps) {
         const int i = i0 + li - 1;
-        for (int j = lane; j < ny; j += 32) Pc[li * pitch + j] = (i >= 0 && i < nx) ? pg[(size_t)i * ny + j] : 0.0;
+        if (i < 0 || i >= nx) continue;
+        for (int j = lane; j < ny; j += 32) Pc[li * pitch + OFF + j] = pg[(size_t)i * ny + j];
+        if (PER && lane == 0) { Pc[li * pitch + 1] = pg[(size_t)i * ny + ny - 1]; Pc[li * pitch + ny + 2] = pg[(size_t)i * ny]; }
     }
     __syncthreads();
 
+    // A pair of cells (indices x, x + 1; x even) of row li: Pc -> Pn, optionally also into a neighbour's halo row.
+    auto pair = [&](int li, int x, uint32_t rem, uint32_t rbar) {
+        const int q = li * pitch + x;
+        const double2 C = *reinterpret_cast<const double2 *>(Pc + q), Nn = *reinterpret_cast<const double2 *>(Pc + q - pitch);
+        const double2 S = *reinterpret_cast<const double2 *>(Pc + q + pitch), B = *reinterpret_cast<const double2 *>(Bs + q);
+        const double W = Pc[q - 1], E = Pc[q + 2];
+        const double r0 = (C.y + W) * cx + (S.x + Nn.x) * cy - B.x;
+        const double r1 = (E + C.x) * cx + (S.y + Nn.y) * cy - B.y;
+        const bool v1 = x + 1 < xend;                       // (odd nj: the last pair has one computed cell)
+        double e0 = W, e1 = v1 ? E : C.y;                   // walls: the edge cells next to the first / last computed cell
+        if (!PER) {
+            if (bk) e0 = bk == 2 ? r0 + (-dy) * bgv : bgv;
+            if (tk) e1 = tk == 2 ? (v1 ? r1 : r0) + dy * tgv : tgv;
+        }
+        const bool first = x == 2, last = x + 2 >= xend;
+        if (v1) *reinterpret_cast<double2 *>(Pn + q) = make_double2(r0, r1);
+        else Pn[q] = r0;
+        if (PER) {
+            if (first) Pn[li * pitch + xend] = r0;                            // copy of column 0 behind the last column
+            if (last) Pn[li * pitch + 1] = v1 ? r1 : r0;                      // copy of column ny-1 in front of the first
+        } else {
+            if (first) Pn[q - 1] = e0;
+            if (last) Pn[li * pitch + xend] = e1;
+        }
+        if (rem) {
+            if (v1) st_async_f64x2(rem + 8u * x, r0, r1, rbar);
+            else st_async_f64(rem + 8u * x, r0, rbar);
+            if (PER) {
+                if (first) st_async_f64(rem + 8u * xend, r0, rbar);
+                if (last) st_async_f64(rem + 8u, v1 ? r1 : r0, rbar);
+            } else {
+                if (first) st_async_f64(rem + 8u * (x - 1), e0, rbar);
+                if (last) st_async_f64(rem + 8u * xend, e1, rbar);
+            }
+        }
+    };
+    const int npairs = (nj + 1) >> 1;
+
+    int gs = 0;                // sweeps done since the launch (hand-off phase)
+#ifdef NNS_X_PROF
+    long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = clock64();
+#define PF(k) do { const long long now_ = clock64(); pf[k] += now_ - pt; pt = now_; } while (0)
+#else
+#define PF(k)
+#endif
     for (int n = 0; n < a.nsteps; ++n) {
         const double *uo = (n & 1) ? us : ug, *vo = (n & 1) ? vs : vg;   // u^n, v^n
         double *un = (n & 1) ? ug : us, *vn = (n & 1) ? vg : vs;         // u^{n+1}
@@ -281,56 +373,90 @@ __global__ void __launch_bounds__(1024, 1) direct_cluster_kernel(const DirectArg
             const int i = i0 + li - 1;
             for (int j = lane; j < ny; j += 32) {
                 double bb = 0.0;
-                if (i > 0 && i < nx - 1 && (per || (j > 0 && j < ny - 1))) {
+                if (i > 0 && i < nx - 1 && (PER || (j > 0 && j < ny - 1))) {
                     const size_t q = (size_t)i * ny + j, rq = (size_t)i * ny;
                     const int jp = j < ny - 1 ? j + 1 : 0, jm = j > 0 ? j - 1 : ny - 1;
                     const double ux = (uo[rq + jp] - uo[rq + jm]) * r2dx, vy = (vo[q + ny] - vo[q - ny]) * r2dy;
                     const double uy = (uo[q + ny] - uo[q - ny]) * r2dy, vx = (vo[rq + jp] - vo[rq + jm]) * r2dx;
                     bb = rho * (rdt * (ux + vy)) - ux * ux - 2.0 * (uy * vx) - vy * vy;
                 }
-                Bs[li * pitch + j] = kb * bb;
+                Bs[li * pitch + OFF + j] = kb * bb;
             }
         }
         __syncthreads();
-        // exactly nit Jacobi sweeps, p BCs after every sweep (direct_fd:76-86), band edges to the neighbours after the BCs
-        for (int s = 0; s < a.g.nit; ++s) {
-            for (int li = 1 + warp; li <= nloc; li += nwarps) {
-                const int i = i0 + li - 1;
-                for (int j = lane; j < ny; j += 32) {
-                    const int q = li * pitch + j;
-                    double rr = Pc[q];
-                    if (i > 0 && i < nx - 1 && (per || (j > 0 && j < ny - 1))) {
-                        const int jp = j < ny - 1 ? j + 1 : 0, jm = j > 0 ? j - 1 : ny - 1;
-                        rr = (Pc[li * pitch + jp] + Pc[li * pitch + jm]) * cx + (Pc[q + pitch] + Pc[q - pitch]) * cy - Bs[q];
+        PF(0);
+        // exactly nit Jacobi sweeps with the p BCs after every sweep (direct_fd:76-86)
+        for (int s = 0; s < a.g.nit; ++s, ++gs) {
+            // 1. the neighbours' edges of the previous sweep; their barriers are armed again for the sweep after this one
+            if (gs > 0) {
+                const int hp = (gs - 1) & 1;
+                if (lane == 0) {
+                    const uint32_t par = (uint32_t)((gs - 1) >> 1) & 1u;
+                    if (has_above) cluster_wait(&hbar[hp][0], par);
+                    if (has_below) cluster_wait(&hbar[hp][1], par);
+                    if (tid == 0) {
+                        if (has_above) mbar_arm(&hbar[hp][0], row_bytes);
+                        if (has_below) mbar_arm(&hbar[hp][1], row_bytes);
                     }
-                    Pn[q] = rr;
                 }
+                __syncwarp();
             }
+            PF(1);
+            // 2. edge rows first: li = 1 (to the CTA above) and li = nloc (to the CTA below)
+            for (int t = tid; t < 2 * npairs; t += blockDim.x) {
+                const bool low = t >= npairs;                          // (nloc >= 3 in every CTA: the launcher checks)
+                const int li = low ? nloc : 1, x = 2 + 2 * (low ? t - npairs : t), i = i0 + li - 1;
+                if (i == 0 || i == nx - 1) continue;                    // global edge rows: copied below, set by the BC replay
+                const uint32_t rem = low ? remB_n : remA_n;
+                pair(li, x, rem, low ? ((gs & 1) ? barB1 : barB0) : ((gs & 1) ? barA1 : barA0));
+            }
+            PF(2);
+            // 3. interior rows of the band (and the copy of a global edge row)
+            for (int li = 2 + warp; li <= nloc - 1; li += nwarps)
+                for (int x = 2 + 2 * lane; x < xend; x += 64) pair(li, x, 0u, 0u);
+            if (i0 == 0)
+                for (int k = tid; k < pitch; k += blockDim.x) Pn[1 * pitch + k] = Pc[1 * pitch + k];
+            if (i1 == nx)
+                for (int k = tid; k < pitch; k += blockDim.x) Pn[nloc * pitch + k] = Pc[nloc * pitch + k];
+            PF(3);
             __syncthreads();
-            band_apply_bc_smem(Pn, nx, ny, pitch, i0, i1, a.pbc, bcval, dx, dy);
-            if (has_above) {          // my first row is the lower halo row (li = band + 1) of the CTA above
-                double *rem = cluster.map_shared_rank(Pn, r - 1);
-                for (int j = tid; j < ny; j += blockDim.x) rem[(band + 1) * pitch + j] = Pn[1 * pitch + j];
+            PF(4);
+            // 4. the BC list where a global edge row is involved
+            if (edge_cta && a.pbc.n > 0) {
+                double *er = Pn + erow * pitch + OFF;
+                const double *ar = Pn + arow * pitch + OFF, *eo = Pc + erow * pitch + OFF, *ao = Pc + arow * pitch + OFF;
+                if (ek)
+                    for (int j = (PER ? 0 : 1) + tid; j < (PER ? ny : ny - 1); j += blockDim.x) er[j] = ek == 2 ? ar[j] + esg * egv : egv;
+                if (!PER && tid >= blockDim.x - 2) {                  // the two corners of the edge row, list order in registers
+                    const bool topc = tid == blockDim.x - 1;
+                    const int jc = topc ? ny - 1 : 0, ji = topc ? ny - 2 : 1, cside = topc ? NNS_SIDE_TOP : NNS_SIDE_BOTTOM;
+                    const double csg = topc ? dy : -dy, a11 = ar[ji];
+                    double t_adj = ao[jc], t_row = eo[ji], c = eo[jc];
+                    for (int k = 0; k < a.pbc.n; ++k) {
+                        const double g = s_pval[k];
+                        const int side = s_pcode[k] & 0xff;
+                        const bool neu = (s_pcode[k] >> 8) == NNS_BC_NEUMANN;
+                        if (side == eside) { t_row = neu ? a11 + esg * g : g; c = neu ? t_adj + esg * g : g; }
+                        else if (side == cside) { t_adj = neu ? a11 + csg * g : g; c = neu ? t_row + csg * g : g; }
+                    }
+                    er[jc] = c;
+                }
+                PF(7);
+                __syncthreads();
             }
-            if (has_below) {          // my last row is the upper halo row (li = 0) of the CTA below
-                double *rem = cluster.map_shared_rank(Pn, r + 1);
-                for (int j = tid; j < ny; j += blockDim.x) rem[j] = Pn[nloc * pitch + j];
-            }
-            __syncthreads();
-            if (tid == 0) {
-                asm volatile("fence.acq_rel.cluster;" ::: "memory");
-                if (has_above) remote_arrive(&hbar[1], (unsigned)(r - 1));     // I am the CTA below of r - 1
-                if (has_below) remote_arrive(&hbar[0], (unsigned)(r + 1));
-            }
-            // The neighbours' edges of this sweep in my halo rows of Pn.  (They overwrite the buffer I read as Pc one
-            // sweep ago: a neighbour only gets there after my arrival of that sweep, i.e. after those reads.)
-            if (tid == 0) {           // one thread acquires at cluster scope, the CTA barrier passes it on
-                if (has_above) cluster_wait(&hbar[0], hpar);
-                if (has_below) cluster_wait(&hbar[1], hpar);
-            }
-            __syncthreads();
-            hpar ^= 1u;
+            PF(5);
             double *t = Pc; Pc = Pn; Pn = t;
+            uint32_t ta = remA_c; remA_c = remA_n; remA_n = ta;
+            ta = remB_c; remB_c = remB_n; remB_n = ta;
+        }
+        // the last sweep's edges of the neighbours are needed by the pressure gradient of my edge rows
+        if (gs > 0) {
+            if (tid == 0) {
+                const uint32_t par = (uint32_t)((gs - 1) >> 1) & 1u;
+                if (has_above) cluster_wait(&hbar[(gs - 1) & 1][0], par);
+                if (has_below) cluster_wait(&hbar[(gs - 1) & 1][1], par);
+            }
+            __syncthreads();
         }
         // velocity update of the own rows (direct_fd:98-118), then u/v BCs (:121-125)
         const double kpx = dt / (2.0 * rho * dx), kpy = dt / (2.0 * rho * dy);
@@ -341,13 +467,13 @@ __global__ void __launch_bounds__(1024, 1) direct_cluster_kernel(const DirectArg
                 const size_t q = (size_t)i * ny + j;
                 const double uc = uo[q], vc = vo[q];
                 double ru = uc, rv = vc;
-                if (i > 0 && i < nx - 1 && (per || (j > 0 && j < ny - 1))) {
-                    const int sq = li * pitch + j;
+                if (i > 0 && i < nx - 1 && (PER || (j > 0 && j < ny - 1))) {
+                    const int row = li * pitch + OFF, sq = row + j;
                     const int jp = j < ny - 1 ? j + 1 : 0, jm = j > 0 ? j - 1 : ny - 1;
                     const size_t rq = (size_t)i * ny;
                     const double uW = uo[rq + jm], uE = uo[rq + jp], uN = uo[q - ny], uS = uo[q + ny];
                     const double vW = vo[rq + jm], vE = vo[rq + jp], vN = vo[q - ny], vS = vo[q + ny];
-                    ru = uc - uc * ax * (uc - uW) - vc * ay * (uc - uN) - kpx * (Pc[li * pitch + jp] - Pc[li * pitch + jm]) +
+                    ru = uc - uc * ax * (uc - uW) - vc * ay * (uc - uN) - kpx * (Pc[row + jp] - Pc[row + jm]) +
                          nu * (kdx * (uE - 2.0 * uc + uW) + kdy * (uS - 2.0 * uc + uN)) + fdt;
                     rv = vc - uc * ax * (vc - vW) - vc * ay * (vc - vN) - kpy * (Pc[sq + pitch] - Pc[sq - pitch]) +
                          nu * (kdx * (vE - 2.0 * vc + vW) + kdy * (vS - 2.0 * vc + vN));
@@ -366,7 +492,7 @@ __global__ void __launch_bounds__(1024, 1) direct_cluster_kernel(const DirectArg
                 const int i = i0 + li - 1;
                 for (int j = lane; j < ny; j += 32) {
                     const size_t q = (size_t)i * ny + j;
-                    const double x = un[q], y = vn[q], z = Pc[li * pitch + j];
+                    const double x = un[q], y = vn[q], z = Pc[li * pitch + OFF + j];
                     if (a.traj_u) { a.traj_u[toff + q] = x; a.traj_v[toff + q] = y; a.traj_p[toff + q] = z; }
                     bad += !(isfinite(x) && isfinite(y) && isfinite(z));
                 }
@@ -376,10 +502,15 @@ __global__ void __launch_bounds__(1024, 1) direct_cluster_kernel(const DirectArg
         // the neighbouring CTAs read my rows of u^{n+1}, v^{n+1} (global memory) in their next RHS / update
         __threadfence();
         cluster.sync();
+        PF(6);
     }
+#ifdef NNS_X_PROF
+    if (tid == 0 && a.nsteps >= 100) printf("cta %d: per sweep: wait %lld edge %lld interior %lld sync %lld+%lld bc %lld | per step: rhs %lld update %lld\n", r,
+        pf[1] / gs, pf[2] / gs, pf[3] / gs, pf[4] / gs, pf[7] / gs, pf[5] / gs, pf[0] / a.nsteps, pf[6] / a.nsteps);
+#endif
     for (int li = 1 + warp; li <= nloc; li += nwarps) {
         const int i = i0 + li - 1;
-        for (int j = lane; j < ny; j += 32) pg[(size_t)i * ny + j] = Pc[li * pitch + j];
+        for (int j = lane; j < ny; j += 32) pg[(size_t)i * ny + j] = Pc[li * pitch + OFF + j];
     }
     if (a.nsteps & 1)
         for (int li = 1 + warp; li <= nloc; li += nwarps) {
@@ -512,20 +643,24 @@ int direct_run(nns_handle *h, double *u, double *v, double *p, int nsteps, doubl
         for (int pass = 0; pass < 2; ++pass)
         for (int nc = 16; nc >= 2; nc /= 2) {
             const int band = (g.nx + nc - 1) / nc;
-            const size_t csmem = sizeof(double) * 3 * (size_t)(band + 2) * pitch;
-            if (band < (pass == 0 ? 8 : 2) || g.nx - (nc - 1) * band < 2 || csmem > (size_t)h->max_smem_optin) continue;
+            const int cpitch = (g.ny + 5) & ~1;             // even, >= ny + 4 (see the kernel's row layout)
+            const size_t csmem = sizeof(double) * 3 * (size_t)(band + 2) * cpitch;
+            // (the first and the last CTA need >= 3 rows: their pushed row must not touch the global edge row, see the kernel)
+            if (band < (pass == 0 ? 8 : 3) || g.nx - (nc - 1) * band < 3 || g.ny < 3 || csmem > (size_t)h->max_smem_optin) continue;
             DirectArgs a{};
             a.g = g; a.ubc = h->bc[0]; a.vbc = h->bc[1]; a.pbc = h->bc[2];
             a.nu_b = h->d_nu; a.bcval = h->d_bcval; a.n_bcs = h->n_bcs;
             a.nsteps = nsteps; a.nsteps_total = nsteps; a.step0 = 0; a.flags = h->params.flags; a.force_x = h->params.force_x;
             a.u = u; a.v = v; a.p = p; a.su = h->d_scratch[0]; a.sv = h->d_scratch[1];
             a.traj_u = tu; a.traj_v = tv; a.traj_p = tp; a.nonfinite = h->d_nonfinite;
-            NNS_CUDA(cudaFuncSetAttribute(direct_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-            if (nc > 8) NNS_CUDA(cudaFuncSetAttribute(direct_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            const bool per = h->params.flags & NNS_FLAG_PERIODIC_X;
+            auto kern = per ? direct_cluster_kernel<true> : direct_cluster_kernel<false>;
+            NNS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+            if (nc > 8) NNS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)(g.batch * nc));
             const char *thr = getenv("NNS_DIRECT_THREADS");        // experiments
-            cfg.blockDim = dim3(thr ? (unsigned)atoi(thr) : 512u);
+            cfg.blockDim = dim3(thr ? (unsigned)std::min(512, std::max(64, atoi(thr) & ~31)) : 512u);
             cfg.dynamicSmemBytes = csmem;
             cfg.stream = st;
             cudaLaunchAttribute attr[1];
@@ -534,11 +669,11 @@ int direct_run(nns_handle *h, double *u, double *v, double *p, int nsteps, doubl
             cfg.attrs = attr;
             cfg.numAttrs = 1;
             int nclusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&nclusters, direct_cluster_kernel, &cfg) != cudaSuccess || nclusters < 1) {
+            if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) {
                 cudaGetLastError();
                 continue;           // this cluster size cannot be scheduled on the device: try the next one / the stream path
             }
-            NNS_CUDA(cudaLaunchKernelEx(&cfg, direct_cluster_kernel, a, band));
+            NNS_CUDA(cudaLaunchKernelEx(&cfg, kern, a, band, cpitch));
             h->launches += 1;
             return NNS_OK;
         }
