@@ -406,8 +406,9 @@ def extra_configs():
             "finite": bool(torch.isfinite(ens.u).all() and torch.isfinite(ens.p).all()),
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "bytes_per_cell_update": 48,
-                         "note": "one 1.5 MB problem on a 16-CTA thread-block cluster (p resident in shared memory): bound by the "
-                                 "shared-memory bandwidth of 16 SMs and the per-sweep hand-off latency, not by HBM"},
+                         "note": "one 1.5 MB problem on a 16-CTA thread-block cluster (p resident in shared memory, band edges by "
+                                 "st.async through distributed shared memory): bound by the shared-memory bandwidth of 16 SMs and "
+                                 "the per-sweep hand-off, not by HBM"},
             "cpu_baseline": {"value": nx * ny * 40 / tc, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": "40 steps in %.2f s (oracle/oracle.c)" % tc}}
         del ens
