@@ -39,7 +39,7 @@ constexpr int RING = GR * NG;   // rows per field in the stencil ring
 #define NNS_REGS_ST 120
 #endif
 constexpr int REGS_SOR = NNS_REGS_SOR, REGS_ST = NNS_REGS_ST;
-constexpr int REGS_SOR_W = 200, REGS_ST_W = 104;     // setmaxnreg only moves registers inside the CTA's launch allocation (384 x 168)
+constexpr int REGS_SOR_W = NNS_REGS_SOR, REGS_ST_W = NNS_REGS_ST;     // setmaxnreg only moves registers inside the CTA's launch allocation (384 x 168)
 constexpr int NW_SOR = NT_SOR / 32;
 constexpr int N_SCRATCH = 4;    // per-CTA scratch sets: launches on different internal streams (nns_chorin_fd_step_host) may overlap
 
