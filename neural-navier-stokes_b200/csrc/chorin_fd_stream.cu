@@ -129,6 +129,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(b))
                  : "memory");
 }
+#ifdef NNS_SOR_STAGE_HANDOFF
 __device__ __forceinline__ void mbar_arrive_release(uint64_t *b) {      // SASS: a bare SYNCS.ARRIVE (no MEMBAR)
     asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
@@ -146,12 +147,10 @@ __device__ __forceinline__ void mbar_wait_acquire(uint64_t *b, uint32_t parity) 
         "r"(parity)
         : "memory");
 }
+#endif
 // 1-D bulk copy shared -> global (bulk async-group completion)
 __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit_wait_all() {
-    asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group 0;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
@@ -186,7 +185,9 @@ __device__ __forceinline__ void wavefront(double (&P)[BR][BC], const double2 *Cm
     // of its waiter.  Bit-identical results, but every warp has 5 of the 7 others as neighbours: it is a CTA barrier
     // built from slower parts (~270 cycles of wait per stage in the trace against ~130 for BAR.SYNC).  Polling progress
     // counters through the LSU instead of mbarriers: 7.6 ms/step (the pollers starve the warps they wait for).
+#if defined(NNS_SOR_STAGE_HANDOFF) || defined(NNS_STREAM_TRACE)
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#endif
     if (owner) publish<BR, BC, 0, BR>(P, h);   // the whole perimeter once
     named_sync(BAR_SOR, NT_SOR);
     const unsigned tolhi = (unsigned)(tolbits >> 32);
