@@ -111,6 +111,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
+#ifdef NNS_DEBUG_TRAP        // a stuck pipeline traps instead of hanging the GPU (experiments)
+    unsigned spins = 0;
+    uint32_t ok = 0;
+    do {
+        asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}"
+                     : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 22)) { printf("mbar_wait stuck: block %d thread %d bar %p parity %u\n", blockIdx.x, threadIdx.x, (void *)b, parity); __trap(); }
+    } while (!ok);
+#else
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
@@ -122,6 +131,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
         "}\n" ::"r"(smem_u32(b)),
         "r"(parity)
         : "memory");
+#endif
 }
 // 1-D bulk copy global -> shared through the TMA unit, completion on an mbarrier (bytes % 16 == 0)
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *b) {
@@ -145,6 +155,18 @@ __device__ __forceinline__ void mbar_wait_acquire(uint64_t *b, uint32_t parity) 
         "WAIT_DONE_A:\n"
         "}\n" ::"r"(smem_u32(b)),
         "r"(parity)
+        : "memory");
+}
+#endif
+#ifdef NNS_SOR_TMEM
+// 16 consecutive 32-bit Tensor Memory columns of the thread's own lane (4 chunks of C')
+__device__ __forceinline__ void tm_st16_top(uint32_t taddr, const double2 (&v)[4]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(__double2loint(v[0].x)), "r"(__double2hiint(v[0].x)), "r"(__double2loint(v[0].y)), "r"(__double2hiint(v[0].y)),
+        "r"(__double2loint(v[1].x)), "r"(__double2hiint(v[1].x)), "r"(__double2loint(v[1].y)), "r"(__double2hiint(v[1].y)),
+        "r"(__double2loint(v[2].x)), "r"(__double2hiint(v[2].x)), "r"(__double2loint(v[2].y)), "r"(__double2hiint(v[2].y)),
+        "r"(__double2loint(v[3].x)), "r"(__double2hiint(v[3].x)), "r"(__double2loint(v[3].y)), "r"(__double2hiint(v[3].y))
         : "memory");
 }
 #endif
@@ -173,7 +195,7 @@ template <int BR, int BC, int RS, int TRACK>
 __device__ __forceinline__ void wavefront(double (&P)[BR][BC], const double2 *Cme, const SHalo<BR, BC> &h, bool owner,
                                           int sd, int tmax, int cap, const Coef &k, unsigned long long tolbits,
                                           unsigned long long &mask, unsigned long long &amb, uint64_t (*hb)[2], unsigned dep, int &gbase,
-                                          long long *prof = nullptr, long long *trace = nullptr) {
+                                          uint32_t tmc, long long *prof = nullptr, long long *trace = nullptr) {
     // One CTA-wide (SOR role) barrier per stage.  EXPERIMENT (-DNNS_SOR_STAGE_HANDOFF, measured slower: 3.94 against 3.62
     // ms/step): point-to-point hand-off instead.  A sub-block sweep of stage T reads what its four neighbours published
     // in stage T-1 and overwrites what they read in stage T-1, so a warp may enter stage T as soon as the warps that hold
@@ -209,6 +231,24 @@ __device__ __forceinline__ void wavefront(double (&P)[BR][BC], const double2 *Cm
         const unsigned nact = __popc(__ballot_sync(0xffffffffu, work));
         if (trace && (threadIdx.x & 31) == 0 && T < TRACE_STAGES) { trace[T * 4 + 0] = clock64(); trace[T * 4 + 2] = nact; }
 #endif
+#ifdef NNS_SOR_TMEM
+        // C' in Tensor Memory: tcgen05.ld is warp-collective, so the whole warp runs the sweep as soon as one lane has work;
+        // the other lanes commit nothing (block_sweep_tmt)
+        if (__any_sync(0xffffffffu, work)) {
+            unsigned mhi = 0u;
+            bool v = false;
+            if (!(q & 1)) block_sweep_tmt<BR, BC, RS, 0, RS, TRACK>(P, tmc, h, k, work, tolbits, mhi, v);
+            else block_sweep_tmt<BR, BC, RS, RS, BR, TRACK>(P, tmc, h, k, work, tolbits, mhi, v);
+            if (work) {
+                if (TRACK == 1) {
+                    mask |= (unsigned long long)(mhi > tolhi) << (q >> 1);
+                    amb |= (unsigned long long)(mhi == tolhi) << (q >> 1);
+                } else if (TRACK == 2) {
+                    mask |= (unsigned long long)v << (q >> 1);
+                }
+            }
+        }
+#else
         if (work) {
             unsigned mhi = 0u;
             bool v = false;
@@ -232,6 +272,7 @@ __device__ __forceinline__ void wavefront(double (&P)[BR][BC], const double2 *Cm
                 mask |= (unsigned long long)v << (q >> 1);
             }
         }
+#endif
 #ifdef NNS_STREAM_TRACE
         __syncwarp();
         if (trace && (threadIdx.x & 31) == 0 && T < TRACE_STAGES) trace[T * 4 + 1] = clock64();
@@ -639,6 +680,20 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
     if (tid < 128) s_ord[tid] = c_ord[tid];
     __syncthreads();
     if (nmine == 0) return;
+#ifdef NNS_SOR_TMEM
+    __shared__ uint32_t s_tmem;
+    if (tid < 32) {         // the whole Tensor Memory of the SM (one CTA per SM): C' of the SOR threads, one lane per thread
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    // lanes 32 * (warp % 4) .. + 31 belong to the warp; SOR warps w and w + 4 share a lane quarter: columns 0 / 128
+    const uint32_t tm_mine = s_tmem + ((uint32_t)(32 * ((tid >> 5) & 3)) << 16) + (uint32_t)(128 * ((tid >> 5) >> 2));
+#else
+    const uint32_t tm_mine = 0u;
+#endif
 
     if (tid >= NT_SOR) {
         // =============================== stencil role ===========================================
@@ -673,7 +728,7 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_SOR));
         SBlock ds = a.desc[tid];
         const bool owner = ds.r0 > 0;
-        if (!owner) { ds.r0 = 1; ds.c0 = 1; }
+        if (!owner) { ds.r0 = 1; ds.c0 = 1; ds.bd = (short)(tid >= NT_SOR / 2); }     // (diagonal parity of the warp: uniform top / bottom choice)
         const int r0 = ds.r0, c0 = ds.c0;
         SHalo<BR, BC> h;
         h.Hme = H + tid;
@@ -716,7 +771,11 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
                 mbar_expect_tx(&s_pfull, (uint32_t)(sizeof(double) * N));
                 bulk_g2s(Cs, pg, (uint32_t)(sizeof(double) * N), &s_pfull);
             }
+#ifdef NNS_SOR_TMEM
+            mbar_wait(&s_pfull, kk & 1);           // (C' does not pass through the region: one phase per member)
+#else
             mbar_wait(&s_pfull, 0);                // phases of s_pfull alternate: p (parity 0), C' image (parity 1)
+#endif
 #pragma unroll
             for (int li = 0; li < BR; ++li)
 #pragma unroll
@@ -742,7 +801,20 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
             named_sync(BAR_READY + (kk & 1), NT_SOR + NT_ST);            // C' image of member kk is complete
             NNS_PROF_ADD(1, t0);
             t0 = NNS_PROF_T();
-#ifndef NNS_SOR_DIRECT_P
+#ifdef NNS_SOR_TMEM
+            {   // the thread's 32 chunks of the image -> its Tensor Memory lane (coalesced 16-byte loads across the warp)
+                const double2 *gi = reinterpret_cast<const double2 *>(img) + tid;
+#pragma unroll 2
+                for (int c = 0; c < NCH; c += 4) {
+                    double2 v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[e] = __ldcg(gi + (size_t)(c + e) * NT_SOR);
+                    tm_st16_top(tm_mine + 4 * c, v);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            }
+            named_sync(BAR_SOR, NT_SOR);
+#elif !defined(NNS_SOR_DIRECT_P)
             // the image has the layout of the C' region: one bulk copy (every SOR thread has left the region: BAR_READY)
             if (tid == 0) {
                 fence_proxy_async();
@@ -791,7 +863,7 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
                     return s_need;
                 };
                 unsigned long long mask = 0ull, amb = 0ull;
-                wavefront<BR, BC, RS, 1>(P, Cme, h, owner, ds.bd, tmax, cap, k, tolbits, mask, amb, s_hb, a.depmask[tid >> 5], gbase,
+                wavefront<BR, BC, RS, 1>(P, Cme, h, owner, ds.bd, tmax, cap, k, tolbits, mask, amb, s_hb, a.depmask[tid >> 5], gbase, tm_mine,
                                      a.prof && (tid == 0 || tid == 128) ? a.prof + (size_t)blockIdx.x * NPROF + 12 + (tid >> 6) : nullptr,
                                      a.trace && blockIdx.x == 0 && kk == 1 ? a.trace + (size_t)(tid >> 5) * TRACE_STAGES * 4 : nullptr);
                 NNS_PROF_ADD(3, t0);
@@ -804,7 +876,7 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
                     // max|dp| of the deciding sweep shares its high word with tol: repeat with the exact test
                     load_block();
                     mask = 0ull; amb = 0ull;
-                    wavefront<BR, BC, RS, 2>(P, Cme, h, owner, ds.bd, tmax, cap, k, tolbits, mask, amb, s_hb, a.depmask[tid >> 5], gbase);
+                    wavefront<BR, BC, RS, 2>(P, Cme, h, owner, ds.bd, tmax, cap, k, tolbits, mask, amb, s_hb, a.depmask[tid >> 5], gbase, tm_mine);
                     need = sweeps_needed(mask, 0ull);
                 }
                 if (need < cap) {
@@ -813,7 +885,7 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
                     load_block();
                     unsigned long long d0 = 0ull, d1 = 0ull;
                     wavefront<BR, BC, RS, 0>(P, Cme, h, owner, ds.bd, 2 * C::NBRc + C::NBCc - 2 + 2 * (need - 1), need, k, tolbits,
-                                         d0, d1, s_hb, a.depmask[tid >> 5], gbase);
+                                         d0, d1, s_hb, a.depmask[tid >> 5], gbase, tm_mine);
                 }
             }
 #ifndef NNS_SOR_DIRECT_P
@@ -860,6 +932,11 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
             NNS_PROF_ADD(5, t0);
         }
     }
+#ifdef NNS_SOR_TMEM
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(512));
+#endif
 }
 
 

@@ -355,4 +355,87 @@ __device__ __forceinline__ void block_sweep_tm(double (&P)[BR][BC], uint32_t tmc
     }
 }
 
+// The same with the exit test of block_sweep (TRACK 0 / 1 / 2): the member-at-a-time kernel with C' in Tensor Memory.
+template <int BR, int BC, int RS, int R0, int R1, int TRACK>
+__device__ __forceinline__ void block_sweep_tmt(double (&P)[BR][BC], uint32_t tmc, const SHalo<BR, BC> &h, const Coef &k,
+                                                bool act, unsigned long long tolbits, unsigned &mhi, bool &viol) {
+    constexpr bool pubTL = true;
+    constexpr int NR = R1 - R0, ND = NR + BC - 1;
+    constexpr int OB = R0 == 0 ? 0 : RS * BC;                  // first cell (consumption order) of this sub-block
+    constexpr int CLO = OB >> 1, CHI = (OB + NR * BC - 1) >> 1, NCQ = CHI - CLO + 1;
+    uint32_t cq[NCQ][4];
+    // last chunk needed by the cells of diagonal kd
+    auto chi = [](int kd) { return (OB + diag_cum<NR, BC>(kd + 1) - 1) >> 1; };
+    auto issue = [&](int from, int to) {       // chunks (from, to]
+#pragma unroll
+        for (int c = CLO; c <= CHI; ++c)
+            if (c > from && c <= to) tm_ld4(tmc + 4 * c, cq[c - CLO]);
+    };
+    auto wait = [&](int from, int to) {
+        bool first = true;
+#pragma unroll
+        for (int c = CLO; c <= CHI; ++c)
+            if (c > from && c <= to) {
+                if (first) tm_wait_ld(cq[c - CLO]);
+                else tm_tie(cq[c - CLO]);
+                first = false;
+            }
+    };
+    const double actf = act ? 1.0 : 0.0;
+    double base[2][NR];
+    auto stageA = [&](int kd, double (&out)[NR]) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int lj = kd - r, li = R0 + r;
+            if (lj >= 0 && lj < BC) {
+                const int o = split_ord<BR, BC, RS>(li, lj);
+                const uint32_t(&c4)[4] = cq[(o >> 1) - CLO];
+                const double cp = (o & 1) ? __hiloint2double((int)c4[3], (int)c4[2]) : __hiloint2double((int)c4[1], (int)c4[0]);
+                const double s = li < BR - 1 ? P[li + 1][lj] : h.hS[lj * NT_SOR];
+                const double e = lj < BC - 1 ? P[li][lj + 1] : h.hE[li * NT_SOR];
+                out[r] = fma(k.ca, s, fma(k.cb, e, fma(k.cc, P[li][lj], -cp)));
+            }
+        }
+    };
+    issue(CLO - 1, chi(1));
+    wait(CLO - 1, chi(1));
+    if (ND > 2) issue(chi(1), chi(2));
+    stageA(0, base[0]);
+#pragma unroll
+    for (int kd = 0; kd < ND; ++kd) {
+        if (kd + 1 < ND) {
+            if (kd >= 1) wait(chi(kd), chi(kd + 1));
+            if (kd >= 1 && kd + 2 < ND) issue(chi(kd + 1), chi(kd + 2));
+            stageA(kd + 1, base[(kd + 1) & 1]);
+        }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int lj = kd - r, li = R0 + r;
+            if (lj >= 0 && lj < BC) {
+                const double n = li > 0 ? P[li - 1][lj] : h.hN[lj * NT_SOR];
+                const double w = lj > 0 ? P[li][lj - 1] : h.hW[li * NT_SOR];
+                const double d = fma(k.ca, n, fma(k.cb, w, base[kd & 1][r]));
+                if (TRACK == 1) mhi = track_hi(mhi, d);
+                if (TRACK == 2) viol |= exceeds_bits(d, tolbits);
+                // p += d for the lanes inside the band, p unchanged (+ 0 * d) for the others: one DFMA, like the
+                // DADD of the legacy sweep and bit-identical to it for actf == 1 (a select would cost two extra
+                // instructions per cell)
+                P[li][lj] = fma(d, actf, P[li][lj]);
+            }
+        }
+    }
+    const bool pT = h.pubT && act && pubTL, pB = h.pubB && act, pL = h.pubL && act && pubTL, pR = h.pubR && act;
+#pragma unroll
+    for (int lj = 0; lj < BC; ++lj) {
+        if (R0 == 0 && pT) h.Hme[lj * NT_SOR] = P[0][lj];
+        if (R1 == BR && pB) h.Hme[(BC + lj) * NT_SOR] = P[BR - 1][lj];
+    }
+#pragma unroll
+    for (int li = R0; li < R1; ++li) {
+        if (pL) h.Hme[(2 * BC + li) * NT_SOR] = P[li][0];
+        if (pR) h.Hme[(2 * BC + BR + li) * NT_SOR] = P[li][BC - 1];
+    }
+}
+
+
 }  // namespace nns
