@@ -444,7 +444,9 @@ int32_t nns_chorin_fd_step_host(nns_handle *h, const double *u, const double *v,
     const double *hin[5] = {u, v, u1, v1, p};
     double *hout[3] = {u_out, v_out, p};
     const int dout[3] = {5, 6, 4};
-    const int nchunks = B >= 1184 ? 8 : B >= 296 ? 2 : 1;     // keep >= 148 CTAs per launch
+    // >= 148 CTAs per launch; many chunks keep the un-overlapped head (first H2D) and tail (last kernel + D2H) short
+    int nchunks = B >= 2368 ? 16 : B >= 1184 ? 8 : B >= 296 ? 2 : 1;
+    if (const char *e = getenv("NNS_STEP_HOST_CHUNKS")) { const int v = atoi(e); if (v >= 1 && (size_t)v <= B) nchunks = v; }     // experiments
     const size_t per = (B + nchunks - 1) / nchunks;
     int rc = reset_nonfinite(h, nullptr);
     if (rc == NNS_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) { set_error("step_host: stream error"); rc = NNS_ERR_CUDA; }
