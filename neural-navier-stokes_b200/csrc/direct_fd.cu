@@ -212,16 +212,28 @@ __device__ __forceinline__ void st_async_f64x2(uint32_t raddr, double v0, double
 __device__ __forceinline__ void mbar_arm(const void *bar, uint32_t bytes) {      // the one expected arrival + the bytes of the next phase
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dsm_u32(bar)), "r"(bytes) : "memory");
 }
+#ifndef NNS_CLUSTER_HINT
+#define NNS_CLUSTER_HINT 100000u
+#endif
 __device__ __forceinline__ void cluster_wait(const void *bar, uint32_t parity) {
     unsigned spins = 0;
     uint32_t ok = 0;
     do {
+#ifdef NNS_CLUSTER_POLL
+        asm volatile(
+            "{\n.reg .pred P1;\n"
+            "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n}"
+            : "=r"(ok) : "r"(dsm_u32(bar)), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 26)) __trap();
+#else
         asm volatile(
             "{\n.reg .pred P1;\n"
             "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, P1;\n}"
-            : "=r"(ok) : "r"(dsm_u32(bar)), "r"(parity), "r"(100000u) : "memory");
-        if (!ok && ++spins > (1u << 16)) __trap();       // a stuck cluster traps instead of hanging the GPU
+            : "=r"(ok) : "r"(dsm_u32(bar)), "r"(parity), "r"(NNS_CLUSTER_HINT) : "memory");
+        if (!ok && ++spins > (1u << 24)) __trap();       // a stuck cluster traps instead of hanging the GPU
+#endif
     } while (!ok);
 }
 
@@ -249,7 +261,11 @@ __device__ __forceinline__ void cluster_wait(const void *bar, uint32_t parity) {
 // two scalar loads for the outer west / east operands (3.5 shared-memory instructions per cell instead of 7):
 //   walls   : JLO = 1, nj = ny-2; index 1 = column 0, index ny = column ny-1 (edge values)        => column j at 1 + j
 //   periodic: JLO = 0, nj = ny;   index 1 = copy of column ny-1, index ny+2 = copy of column 0    => column j at 2 + j
-template <bool PER>
+// NPT > 0: every thread owns up to NPT fixed pairs of the band (pair index tid + k * blockDim.x, the two edge rows first)
+// and keeps their p and b values in registers over the sweeps: a sweep then reads only the north / south pairs and the
+// outer west / east cells from shared memory (64 instead of 96 bytes per pair), and the work is spread evenly over the
+// threads.  NPT = 0: rows per warp, everything from shared memory (bands with more pairs per thread than the instantiated NPT).
+template <bool PER, int NPT>
 __global__ void __launch_bounds__(512, 1) direct_cluster_kernel(const DirectArgs a, int band, int pitch) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) unsigned long long hbar[2][2];    // [sweep parity][0: from the CTA above, 1: from the CTA below]
@@ -320,11 +336,11 @@ __global__ void __launch_bounds__(512, 1) direct_cluster_kernel(const DirectArgs
     }
     __syncthreads();
 
-    // A pair of cells (indices x, x + 1; x even) of row li: Pc -> Pn, optionally also into a neighbour's halo row.
-    auto pair = [&](int li, int x, uint32_t rem, uint32_t rbar) {
+    // A pair of cells (indices x, x + 1; x even) of row li: Pc -> Pn, optionally also into a neighbour's halo row.  C, B: the
+    // pair's own p and b values; returns its new p values (the second one is the edge cell's if the pair has one computed cell).
+    auto pair_core = [&](int li, int x, double2 C, double2 B, uint32_t rem, uint32_t rbar) -> double2 {
         const int q = li * pitch + x;
-        const double2 C = *reinterpret_cast<const double2 *>(Pc + q), Nn = *reinterpret_cast<const double2 *>(Pc + q - pitch);
-        const double2 S = *reinterpret_cast<const double2 *>(Pc + q + pitch), B = *reinterpret_cast<const double2 *>(Bs + q);
+        const double2 Nn = *reinterpret_cast<const double2 *>(Pc + q - pitch), S = *reinterpret_cast<const double2 *>(Pc + q + pitch);
         const double W = Pc[q - 1], E = Pc[q + 2];
         const double r0 = (C.y + W) * cx + (S.x + Nn.x) * cy - B.x;
         const double r1 = (E + C.x) * cx + (S.y + Nn.y) * cy - B.y;
@@ -355,8 +371,26 @@ __global__ void __launch_bounds__(512, 1) direct_cluster_kernel(const DirectArgs
                 if (last) st_async_f64(rem + 8u * xend, e1, rbar);
             }
         }
+        return make_double2(r0, v1 ? r1 : e1);
+    };
+    auto pair = [&](int li, int x, uint32_t rem, uint32_t rbar) {
+        const int q = li * pitch + x;
+        pair_core(li, x, *reinterpret_cast<const double2 *>(Pc + q), *reinterpret_cast<const double2 *>(Bs + q), rem, rbar);
     };
     const int npairs = (nj + 1) >> 1;
+    // NPT > 0: this thread's pairs.  Pair index -> row: 0 .. npairs-1 row 1, npairs .. 2 npairs - 1 row nloc, then rows 2 .. nloc-1
+    constexpr int NPTA = NPT > 0 ? NPT : 1;
+    int pli[NPTA], px[NPTA];                 // row (0 = no pair) and first index of the pair
+    double2 Ck[NPTA], Bk[NPTA];
+#pragma unroll
+    for (int k = 0; k < NPTA; ++k) {
+        const int idx = tid + k * (int)blockDim.x, rs = idx / npairs;
+        const int li = rs == 0 ? 1 : rs == 1 ? nloc : rs;
+        const int i = i0 + li - 1;
+        pli[k] = (NPT > 0 && rs < nloc && i != 0 && i != nx - 1) ? li : 0;
+        px[k] = 2 + 2 * (idx - rs * npairs);
+        Ck[k] = make_double2(0.0, 0.0); Bk[k] = make_double2(0.0, 0.0);
+    }
 
     int gs = 0;                // sweeps done since the launch (hand-off phase)
 #ifdef NNS_X_PROF
@@ -384,6 +418,15 @@ __global__ void __launch_bounds__(512, 1) direct_cluster_kernel(const DirectArgs
             }
         }
         __syncthreads();
+        if (NPT > 0) {
+#pragma unroll
+            for (int k = 0; k < NPTA; ++k)
+                if (pli[k]) {
+                    const int q = pli[k] * pitch + px[k];
+                    Bk[k] = *reinterpret_cast<const double2 *>(Bs + q);
+                    Ck[k] = *reinterpret_cast<const double2 *>(Pc + q);
+                }
+        }
         PF(0);
         // exactly nit Jacobi sweeps with the p BCs after every sweep (direct_fd:76-86)
         for (int s = 0; s < a.g.nit; ++s, ++gs) {
@@ -402,6 +445,20 @@ __global__ void __launch_bounds__(512, 1) direct_cluster_kernel(const DirectArgs
                 __syncwarp();
             }
             PF(1);
+            if (NPT > 0) {
+                // 2. + 3. the thread's own pairs, p and b from registers (k = 0 holds the edge-row pairs: they go out first)
+#pragma unroll
+                for (int k = 0; k < NPTA; ++k) {
+                    if (k == 1) PF(2);
+                    if (pli[k]) {
+                        const int li = pli[k], x = px[k];
+                        if (PER && x + 1 >= xend) Ck[k].y = Pc[li * pitch + x + 1];       // (odd ny: the wrap copy next to the last cell)
+                        const uint32_t rem = li == 1 ? remA_n : li == nloc ? remB_n : 0u;       // (0 without that neighbour)
+                        const uint32_t rbar = li == 1 ? ((gs & 1) ? barA1 : barA0) : ((gs & 1) ? barB1 : barB0);
+                        Ck[k] = pair_core(li, x, Ck[k], Bk[k], rem, rbar);
+                    }
+                }
+            } else {
             // 2. edge rows first: li = 1 (to the CTA above) and li = nloc (to the CTA below)
             for (int t = tid; t < 2 * npairs; t += blockDim.x) {
                 const bool low = t >= npairs;                          // (nloc >= 3 in every CTA: the launcher checks)
@@ -414,6 +471,7 @@ __global__ void __launch_bounds__(512, 1) direct_cluster_kernel(const DirectArgs
             // 3. interior rows of the band (and the copy of a global edge row)
             for (int li = 2 + warp; li <= nloc - 1; li += nwarps)
                 for (int x = 2 + 2 * lane; x < xend; x += 64) pair(li, x, 0u, 0u);
+            }
             if (i0 == 0)
                 for (int k = tid; k < pitch; k += blockDim.x) Pn[1 * pitch + k] = Pc[1 * pitch + k];
             if (i1 == nx)
@@ -654,13 +712,22 @@ int direct_run(nns_handle *h, double *u, double *v, double *p, int nsteps, doubl
             a.u = u; a.v = v; a.p = p; a.su = h->d_scratch[0]; a.sv = h->d_scratch[1];
             a.traj_u = tu; a.traj_v = tv; a.traj_p = tp; a.nonfinite = h->d_nonfinite;
             const bool per = h->params.flags & NNS_FLAG_PERIODIC_X;
-            auto kern = per ? direct_cluster_kernel<true> : direct_cluster_kernel<false>;
+            const char *thr = getenv("NNS_DIRECT_THREADS");        // experiments
+            const int nthreads = thr ? std::min(512, std::max(64, atoi(thr) & ~31)) : 512;
+            const int npairs = ((per ? g.ny : g.ny - 2) + 1) / 2;
+            // p / b of a thread's pairs in registers: measured 0.079 against 0.085 ms/step on the periodic channel, 0.107
+            // against 0.104 on the cavity (256 x 256; the sweep period is set by the neighbour hand-off, not by the
+            // shared-memory traffic it saves) -- used for the periodic variant; NNS_DIRECT_NPT = 0 / 4 forces either
+            const char *npt_env = getenv("NNS_DIRECT_NPT");
+            const bool fits4 = (long)band * npairs <= 4L * nthreads;
+            const bool regs4 = fits4 && (npt_env ? atoi(npt_env) == 4 : per);
+            auto kern = per ? (regs4 ? direct_cluster_kernel<true, 4> : direct_cluster_kernel<true, 0>)
+                            : (regs4 ? direct_cluster_kernel<false, 4> : direct_cluster_kernel<false, 0>);
             NNS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
             if (nc > 8) NNS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)(g.batch * nc));
-            const char *thr = getenv("NNS_DIRECT_THREADS");        // experiments
-            cfg.blockDim = dim3(thr ? (unsigned)std::min(512, std::max(64, atoi(thr) & ~31)) : 512u);
+            cfg.blockDim = dim3((unsigned)nthreads);
             cfg.dynamicSmemBytes = csmem;
             cfg.stream = st;
             cudaLaunchAttribute attr[1];
