@@ -450,7 +450,11 @@ __global__ void __launch_bounds__(512, 1) direct_cluster_kernel(const DirectArgs
 #pragma unroll
                 for (int k = 0; k < NPTA; ++k) {
                     if (k == 1) PF(2);
+#ifdef NNS_X_EDGEONLY       // timing experiment: only the pushed rows are computed (wrong results): period = hand-off latency
+                    if (pli[k] && (pli[k] == 1 || pli[k] == nloc)) {
+#else
                     if (pli[k]) {
+#endif
                         const int li = pli[k], x = px[k];
                         if (PER && x + 1 >= xend) Ck[k].y = Pc[li * pitch + x + 1];       // (odd ny: the wrap copy next to the last cell)
                         const uint32_t rem = li == 1 ? remA_n : li == nloc ? remB_n : 0u;       // (0 without that neighbour)

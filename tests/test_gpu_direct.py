@@ -77,15 +77,17 @@ def test_direct_chip_cluster_and_stream_paths_agree(oracle_fd, monkeypatch, shap
     nus = np.array([0.05, 0.1, 0.02])
     f = [np.stack([smooth_ic(nx, ny, 40 + 3 * b + k, amp=0.1)[0] for b in range(B)]) for k in range(3)]
     out = {}
-    for mode in ("chip", "cluster", "stream"):
-        monkeypatch.setenv("NNS_DIRECT_MODE", mode)
+    for mode in ("chip", "cluster", "cluster_regs", "stream"):
+        monkeypatch.setenv("NNS_DIRECT_MODE", mode.split("_")[0])
+        monkeypatch.setenv("NNS_DIRECT_NPT", "4" if mode == "cluster_regs" else "0")     # p / b of a thread's pairs in registers
         ens = DirectEnsemble(B, nx, ny, u_bc=u_bc, v_bc=v_bc, p_bc=p_bc, nit=7, dt=2e-4, rho=1.1, nu=nus)
         ens.set_state(*f)
         tu, tv, tp = ens.run(5, trajectory=True)
         torch.cuda.synchronize()
         out[mode] = (tu.clone(), tv.clone(), tp.clone(), ens.u.clone(), ens.v.clone(), ens.p.clone(), ens.launches)
     monkeypatch.delenv("NNS_DIRECT_MODE")
-    assert out["chip"][6] == 1 and out["cluster"][6] == 1 and out["stream"][6] > 50     # the three paths really ran
+    monkeypatch.delenv("NNS_DIRECT_NPT")
+    assert out["chip"][6] == 1 and out["cluster"][6] == 1 and out["cluster_regs"][6] == 1 and out["stream"][6] > 50     # the paths really ran
     for b in range(B):
         u, v, p = oracle_fd.direct_simulate(f[0][b], f[1][b], f[2][b], u_bc, v_bc, p_bc, nt=5, nit=7, dt=2e-4,
                                             rho=1.1, nu=nus[b])
@@ -95,12 +97,12 @@ def test_direct_chip_cluster_and_stream_paths_agree(oracle_fd, monkeypatch, shap
             assert rel_l2(tp[b].cpu().numpy(), p) <= TOL, mode
             assert rel_l2(out[mode][3][b].cpu().numpy(), u[-1]) <= TOL and rel_l2(out[mode][5][b].cpu().numpy(), p[-1]) <= TOL
     for k in range(6):
-        for other in ("cluster", "stream"):
+        for other in ("cluster", "cluster_regs", "stream"):
             d = float((out["chip"][k] - out[other][k]).norm() / out["chip"][k].norm())
             assert d <= 1e-13, (k, other, d)
 
 
-@pytest.mark.parametrize("shape,mode", [((41, 48), "chip"), ((96, 128), "cluster"), ((256, 256), "cluster")])
+@pytest.mark.parametrize("shape,mode", [((41, 48), "chip"), ((96, 128), "cluster"), ((96, 127), "cluster"), ((256, 256), "cluster")])
 def test_direct_periodic_channel_extension(oracle_fd, monkeypatch, shape, mode):
     """BASELINE config 2b: channel flow, periodic in the differenced axis 1 with a body force (an EXTENSION: the reference
     has neither; reference-unpinned).  Oracle = numpy restatement of direct_fd:56-127 with wrapped column indices
