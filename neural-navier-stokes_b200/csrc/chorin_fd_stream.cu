@@ -742,7 +742,12 @@ __global__ void __launch_bounds__(NT_SOR + NT_ST, 1) chorin_stream_kernel(const 
         const double dx = a.g.dx, dy = a.g.dy, beta = a.g.beta;
         const double dx2 = dx * dx, dy2 = dy * dy, den = 2.0 * dx2 + 2.0 * dy2;
         Coef k;
-        k.ca = beta * dy2 / den; k.cb = beta * dx2 / den; k.cc = -beta; k.cu = 0; k.cv = 0; k.beta = beta; k.tol = a.g.tol;
+        k.ca = beta * dy2 / den; k.cb = beta * dx2 / den; k.cu = 0; k.cv = 0; k.beta = beta; k.tol = a.g.tol;
+#ifdef NNS_SOR_FORM_PN
+        k.cc = 1.0 - beta;
+#else
+        k.cc = -beta;
+#endif
         const unsigned long long tolbits = (unsigned long long)__double_as_longlong(a.g.tol);
         const int cap = a.g.nit - 1;
         const int tmax = 2 * C::NBRc + C::NBCc - 2 + 2 * (cap - 1);      // last sub-block diagonal + 2 (cap - 1)
