@@ -203,6 +203,21 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local, unsigned rank) {
 // Asynchronous store into a neighbouring CTA's shared memory that completes (transaction bytes) on an mbarrier of that
 // CTA: the consumer that sees the phase complete sees the data -- no fence on either side.  (A release arrive or a fence at
 // cluster scope compiles to MEMBAR.ALL.GPU + CCTL.IVALL: three of those per warp and sweep were half of the sweep time.)
+#ifdef NNS_CLUSTER_PLAIN_ST
+// EXPERIMENT: plain stores through distributed shared memory; after a CTA barrier ONE thread issues fence.release.cluster
+// (MEMBAR.ALL.GPU, once per sweep and CTA instead of three times per warp as in the first version) and a relaxed arrive (a
+// bare SYNCS.ARRIVE) on each neighbour's mbarrier.
+__device__ __forceinline__ void st_async_f64(uint32_t raddr, double v, uint32_t) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(raddr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st_async_f64x2(uint32_t raddr, double v0, double v1, uint32_t) {
+    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(raddr), "d"(v0), "d"(v1) : "memory");
+}
+__device__ __forceinline__ void mbar_arm(const void *, uint32_t) {}
+__device__ __forceinline__ void remote_arrive_relaxed(uint32_t rbar) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+}
+#else
 __device__ __forceinline__ void st_async_f64(uint32_t raddr, double v, uint32_t rbar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(raddr), "d"(v), "r"(rbar) : "memory");
 }
@@ -212,6 +227,7 @@ __device__ __forceinline__ void st_async_f64x2(uint32_t raddr, double v0, double
 __device__ __forceinline__ void mbar_arm(const void *bar, uint32_t bytes) {      // the one expected arrival + the bytes of the next phase
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dsm_u32(bar)), "r"(bytes) : "memory");
 }
+#endif
 #ifndef NNS_CLUSTER_HINT
 #define NNS_CLUSTER_HINT 100000u
 #endif
@@ -449,7 +465,19 @@ __global__ void __launch_bounds__(512, 1) direct_cluster_kernel(const DirectArgs
                 // 2. + 3. the thread's own pairs, p and b from registers (k = 0 holds the edge-row pairs: they go out first)
 #pragma unroll
                 for (int k = 0; k < NPTA; ++k) {
-                    if (k == 1) PF(2);
+                    if (k == 1) {
+#ifdef NNS_CLUSTER_PLAIN_ST
+                        if (has_above || has_below) {
+                            asm volatile("bar.sync 1, %0;" ::"r"((int)blockDim.x) : "memory");           // every thread's edge-row stores are issued
+                            if (tid == 0) {
+                                asm volatile("fence.release.cluster;" ::: "memory");
+                                if (has_above) remote_arrive_relaxed((gs & 1) ? barA1 : barA0);
+                                if (has_below) remote_arrive_relaxed((gs & 1) ? barB1 : barB0);
+                            }
+                        }
+#endif
+                        PF(2);
+                    }
 #ifdef NNS_X_EDGEONLY       // timing experiment: only the pushed rows are computed (wrong results): period = hand-off latency
                     if (pli[k] && (pli[k] == 1 || pli[k] == nloc)) {
 #else
@@ -471,6 +499,16 @@ __global__ void __launch_bounds__(512, 1) direct_cluster_kernel(const DirectArgs
                 const uint32_t rem = low ? remB_n : remA_n;
                 pair(li, x, rem, low ? ((gs & 1) ? barB1 : barB0) : ((gs & 1) ? barA1 : barA0));
             }
+#ifdef NNS_CLUSTER_PLAIN_ST
+            if (has_above || has_below) {
+                asm volatile("bar.sync 1, %0;" ::"r"((int)blockDim.x) : "memory");           // every thread's edge-row stores are issued
+                if (tid == 0) {
+                    asm volatile("fence.release.cluster;" ::: "memory");
+                    if (has_above) remote_arrive_relaxed((gs & 1) ? barA1 : barA0);
+                    if (has_below) remote_arrive_relaxed((gs & 1) ? barB1 : barB0);
+                }
+            }
+#endif
             PF(2);
             // 3. interior rows of the band (and the copy of a global edge row)
             for (int li = 2 + warp; li <= nloc - 1; li += nwarps)
