@@ -841,6 +841,57 @@ __global__ void dslab_jacobi_kernel(SlabGeom g, const double *__restrict__ pc, c
     pn[q] = r;
 }
 
+// The Jacobi sweep with the p BC list applied in the same launch (the list walk above costs one launch per entry and
+// sweep: at 8 GPUs the launches took longer than the sweeps).  Only the four corner cells of the grid depend on the
+// order of the list (boundary.py:34-86 applied in list order): a cell of column 0 / ny-1 in another row is written by
+// bottom / top entries only and reads the new value next to it, a non-corner cell of row 0 / nx-1 by left / right entries
+// only and reads the new value of the adjacent row -- the LAST entry of that side decides, and the thread recomputes the
+// neighbour's new value (same device function: same bits).  A corner thread replays the list in registers on the corner
+// and its two neighbours (their values before the first entry are the previous sweep's: edge cells are copied through).
+struct DirectBcPlan {
+    int n;
+    int side[NNS_MAX_BC], neu[NNS_MAX_BC];
+    double val[NNS_MAX_BC];
+    int kind[4];                 // per side (NNS_SIDE_*): 0 none, 1 Dirichlet, 2 Neumann -- the last entry of that side
+    double g[4];
+};
+
+__device__ __forceinline__ double dslab_jac(const double *__restrict__ pc, const double *__restrict__ bs, size_t q, int ny,
+                                            double cx, double cy) {
+    return (pc[q + 1] + pc[q - 1]) * cx + (pc[q + ny] + pc[q - ny]) * cy - bs[q];
+}
+
+__global__ void dslab_jacobi_bc_kernel(SlabGeom g, DirectBcPlan bc, const double *__restrict__ pc, const double *__restrict__ bs,
+                                       double *__restrict__ pn) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = g.row0 + blockIdx.y;
+    if (j >= g.ny || i >= g.row1) return;
+    const size_t q = g.v.at(i, j);
+    const int ny = g.ny, nx = g.nx;
+    const double dx2 = g.dx * g.dx, dy2 = g.dy * g.dy;
+    const double rden = 1.0 / (2.0 * (dx2 + dy2));
+    const double cx = dy2 * rden, cy = dx2 * rden;
+    const bool rowe = i == 0 || i == nx - 1, cole = j == 0 || j == ny - 1;
+    if (!rowe && !cole) { pn[q] = dslab_jac(pc, bs, q, ny, cx, cy); return; }
+    const int rside = i == 0 ? NNS_SIDE_LEFT : NNS_SIDE_RIGHT, cside = j == 0 ? NNS_SIDE_BOTTOM : NNS_SIDE_TOP;
+    const int ii = i == 0 ? 1 : nx - 2, ji = j == 0 ? 1 : ny - 2;          // the adjacent interior row / column
+    const double rsg = i == 0 ? -g.dx : g.dx, csg = j == 0 ? -g.dy : g.dy;
+    double r = pc[q];
+    if (cole && !rowe) {
+        if (bc.kind[cside]) r = bc.kind[cside] == 2 ? dslab_jac(pc, bs, g.v.at(i, ji), ny, cx, cy) + csg * bc.g[cside] : bc.g[cside];
+    } else if (rowe && !cole) {
+        if (bc.kind[rside]) r = bc.kind[rside] == 2 ? dslab_jac(pc, bs, g.v.at(ii, j), ny, cx, cy) + rsg * bc.g[rside] : bc.g[rside];
+    } else {
+        const double a11 = dslab_jac(pc, bs, g.v.at(ii, ji), ny, cx, cy);
+        double t_adj = pc[g.v.at(ii, j)], t_row = pc[g.v.at(i, ji)];
+        for (int k = 0; k < bc.n; ++k) {
+            const double gv = bc.val[k];
+            if (bc.side[k] == rside) { t_row = bc.neu[k] ? a11 + rsg * gv : gv; r = bc.neu[k] ? t_adj + rsg * gv : gv; }
+            else if (bc.side[k] == cside) { t_adj = bc.neu[k] ? a11 + csg * gv : gv; r = bc.neu[k] ? t_row + csg * gv : gv; }
+        }
+    }
+    pn[q] = r;
+}
+
 __global__ void dslab_update_kernel(SlabGeom g, const double *__restrict__ uo, const double *__restrict__ vo,
                                     const double *__restrict__ p, double *__restrict__ un, double *__restrict__ vn,
                                     unsigned long long *nonfinite, int check) {
@@ -881,12 +932,33 @@ int direct_slab_run(nns_handle *h, double *u, double *v, double *p, int nsteps, 
         if (!S->d_own[k]) { NNS_CUDA(cudaMalloc(&S->d_own[k], bytes)); NNS_CUDA(cudaMemsetAsync(S->d_own[k], 0, bytes, st)); }
     double *uc = u, *vc = v, *un = S->d_own[0], *vn = S->d_own[1], *pn = S->d_own[2], *b = S->d_own[3], *pc = p;
     int rc;
+    // p BCs inside the sweep kernel: the rank that owns a global edge row needs the adjacent interior row too (it recomputes
+    // that row's new value); NNS_DSLAB_BC=list keeps the list walk (one launch per entry) for tests
+    DirectBcPlan plan{};
+    {
+        const BcList &L = h->bc[2];
+        plan.n = L.n;
+        for (int k = 0; k < L.n; ++k) {
+            plan.side[k] = L.side[k]; plan.neu[k] = L.type[k] == NNS_BC_NEUMANN; plan.val[k] = L.value[k];
+            plan.kind[L.side[k]] = plan.neu[k] ? 2 : 1; plan.g[L.side[k]] = L.value[k];
+        }
+    }
+    const char *bcm = getenv("NNS_DSLAB_BC");
+    const bool owns_top = S->row0 == 0, owns_bot = S->row0 + S->nrows == G.nx;
+    const bool fused_bc = !(bcm && strcmp(bcm, "list") == 0) && G.nx >= 4 && G.ny >= 3 &&
+                          (!owns_top || S->nrows >= 2) && (!owns_bot || S->nrows >= 2);
     for (int n = 0; n < nsteps; ++n) {
         dslab_rhs_kernel<<<grd, blk, 0, st>>>(g, uc, vc, b);
         for (int s = 0; s < G.nit; ++s) {
-            dslab_jacobi_kernel<<<grd, blk, 0, st>>>(g, pc, b, pn);
-            h->launches += 1;
-            if ((rc = apply_bc_list(h, g, 2, pn, st)) || (rc = exchange_rows(h, S, pn, st))) return rc;
+            if (fused_bc) {
+                dslab_jacobi_bc_kernel<<<grd, blk, 0, st>>>(g, plan, pc, b, pn);
+                h->launches += 1;
+            } else {
+                dslab_jacobi_kernel<<<grd, blk, 0, st>>>(g, pc, b, pn);
+                h->launches += 1;
+                if ((rc = apply_bc_list(h, g, 2, pn, st))) return rc;
+            }
+            if ((rc = exchange_rows(h, S, pn, st))) return rc;
             double *t = pc; pc = pn; pn = t;
         }
         dslab_update_kernel<<<grd, blk, 0, st>>>(g, uc, vc, pc, un, vn, h->d_nonfinite, h->params.flags & NNS_FLAG_CHECK_FINITE);

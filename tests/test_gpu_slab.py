@@ -231,3 +231,28 @@ def test_direct_fd_slabs_vs_oracle(oracle_fd, world):
     ou, ov, op = oracle_fd.direct_simulate(ic[0].copy(), ic[1].copy(), ic[2].copy(), _t(u_bc), _t(v_bc), _t(p_bc), nt=nsteps,
                                            nit=9, dt=1e-4, rho=1.1, nu=0.05)
     assert rel_l2(u, ou[-1]) <= TOL and rel_l2(v, ov[-1]) <= TOL and rel_l2(p, op[-1]) <= TOL
+
+
+def test_direct_fd_slab_fused_bcs_equal_list_walk(oracle_fd, monkeypatch):
+    """The p BCs applied inside the Jacobi kernel (last entry per side + corner replay in registers) against the list walk
+    with one launch per entry (NNS_DSLAB_BC=list): mixed BC order with non-zero Neumann values, same results to rounding."""
+    from nns_b200.slab import SlabDirect
+    nx, ny, nsteps = 70, 90, 3
+    u_bc, v_bc, p_bc = _bcs(nx, ny, "mixed")
+    ic = smooth_ic(nx, ny, 5, amp=0.1)
+    out = {}
+    for mode in ("fused", "list"):
+        monkeypatch.setenv("NNS_DSLAB_BC", mode)
+        sl = SlabDirect(nx, ny, u_bc=u_bc, v_bc=v_bc, p_bc=p_bc, nit=7, dt=1e-4, rho=1.1, nu=0.05, rank=0, world=1)
+        sl.set_state(*ic)
+        sl.sync_halos()
+        l0 = sl.launches
+        sl.run(nsteps)
+        out[mode] = (sl.gather(sl.u), sl.gather(sl.v), sl.gather(sl.p), sl.launches - l0)
+    monkeypatch.delenv("NNS_DSLAB_BC")
+    assert out["fused"][3] < out["list"][3]                   # the list walk really launches a kernel per entry
+    for k in range(3):
+        assert rel_l2(out["fused"][k], out["list"][k]) <= 1e-13
+    ou, ov, op = oracle_fd.direct_simulate(ic[0].copy(), ic[1].copy(), ic[2].copy(), _t(u_bc), _t(v_bc), _t(p_bc), nt=nsteps,
+                                           nit=7, dt=1e-4, rho=1.1, nu=0.05)
+    assert rel_l2(out["fused"][2], op[-1]) <= TOL and rel_l2(out["fused"][0], ou[-1]) <= TOL
