@@ -98,6 +98,8 @@ struct SlabState {
     unsigned char *peer_box[2] = {nullptr, nullptr};   // mapped mailboxes of the rank above (0) / below (1)
     bool p2p = false;
     unsigned seq = 0;                         // tick sequence number (monotonic over the run)
+    cudaStream_t st_x = nullptr;              // direct_fd slabs: exchange stream (halo rows under the interior sweep)
+    cudaEvent_t ev_edge = nullptr, ev_xdone = nullptr;
     CUresult (*StreamWaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
     int last_ticks = 0;
 };
@@ -634,6 +636,9 @@ void slab_free(nns_handle *h) {
     for (int d = 0; d < 2; ++d) if (S->peer_box[d]) cudaIpcCloseMemHandle(S->peer_box[d]);
     cudaFree(S->d_box);
     if (S->h_flags) cudaFreeHost(S->h_flags);
+    if (S->ev_edge) cudaEventDestroy(S->ev_edge);
+    if (S->ev_xdone) cudaEventDestroy(S->ev_xdone);
+    if (S->st_x) cudaStreamDestroy(S->st_x);
     if (S->ev[0]) cudaEventDestroy(S->ev[0]);
     if (S->ev[1]) cudaEventDestroy(S->ev[1]);
     delete S;
@@ -861,10 +866,13 @@ __device__ __forceinline__ double dslab_jac(const double *__restrict__ pc, const
     return (pc[q + 1] + pc[q - 1]) * cx + (pc[q + ny] + pc[q - ny]) * cy - bs[q];
 }
 
+// rows: ra >= 0: the two rows ra, rb (blockIdx.y = 0 / 1: the slab's edge rows, swept first so that their exchange runs
+// under the interior sweep); else the rows g.row0 + roff + blockIdx.y
 __global__ void dslab_jacobi_bc_kernel(SlabGeom g, DirectBcPlan bc, const double *__restrict__ pc, const double *__restrict__ bs,
-                                       double *__restrict__ pn) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = g.row0 + blockIdx.y;
-    if (j >= g.ny || i >= g.row1) return;
+                                       double *__restrict__ pn, int ra, int rb, int roff, int rend) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = ra >= 0 ? (blockIdx.y == 0 ? ra : rb) : g.row0 + roff + (int)blockIdx.y;
+    if (j >= g.ny || i >= (ra >= 0 ? g.row1 : rend)) return;
     const size_t q = g.v.at(i, j);
     const int ny = g.ny, nx = g.nx;
     const double dx2 = g.dx * g.dx, dy2 = g.dy * g.dy;
@@ -947,11 +955,32 @@ int direct_slab_run(nns_handle *h, double *u, double *v, double *p, int nsteps, 
     const bool owns_top = S->row0 == 0, owns_bot = S->row0 + S->nrows == G.nx;
     const bool fused_bc = !(bcm && strcmp(bcm, "list") == 0) && G.nx >= 4 && G.ny >= 3 &&
                           (!owns_top || S->nrows >= 2) && (!owns_bot || S->nrows >= 2);
+    // several ranks: sweep the slab's first and last row first and exchange them (second stream) under the interior sweep
+    const char *ovl = getenv("NNS_DSLAB_OVERLAP");
+    const bool overlap = fused_bc && S->nranks > 1 && S->nrows >= 4 && (ovl && atoi(ovl) == 1);      // opt-in until measured on a multi-GPU box
+    if (overlap && !S->st_x) {
+        NNS_CUDA(cudaStreamCreateWithFlags(&S->st_x, cudaStreamNonBlocking));
+        NNS_CUDA(cudaEventCreateWithFlags(&S->ev_edge, cudaEventDisableTiming));
+        NNS_CUDA(cudaEventCreateWithFlags(&S->ev_xdone, cudaEventDisableTiming));
+    }
     for (int n = 0; n < nsteps; ++n) {
         dslab_rhs_kernel<<<grd, blk, 0, st>>>(g, uc, vc, b);
         for (int s = 0; s < G.nit; ++s) {
+            if (fused_bc && overlap) {
+                // edge rows, their exchange on the second stream, the interior rows meanwhile on the first
+                dslab_jacobi_bc_kernel<<<dim3(grd.x, 2), blk, 0, st>>>(g, plan, pc, b, pn, g.row0, g.row1 - 1, 0, 0);
+                NNS_CUDA(cudaEventRecord(S->ev_edge, st));
+                NNS_CUDA(cudaStreamWaitEvent(S->st_x, S->ev_edge, 0));
+                if ((rc = exchange_rows(h, S, pn, S->st_x))) return rc;
+                NNS_CUDA(cudaEventRecord(S->ev_xdone, S->st_x));
+                dslab_jacobi_bc_kernel<<<dim3(grd.x, S->nrows - 2), blk, 0, st>>>(g, plan, pc, b, pn, -1, -1, 1, g.row1 - 1);
+                NNS_CUDA(cudaStreamWaitEvent(st, S->ev_xdone, 0));
+                h->launches += 2;
+                double *t = pc; pc = pn; pn = t;
+                continue;
+            }
             if (fused_bc) {
-                dslab_jacobi_bc_kernel<<<grd, blk, 0, st>>>(g, plan, pc, b, pn);
+                dslab_jacobi_bc_kernel<<<grd, blk, 0, st>>>(g, plan, pc, b, pn, -1, -1, 0, g.row1);
                 h->launches += 1;
             } else {
                 dslab_jacobi_kernel<<<grd, blk, 0, st>>>(g, pc, b, pn);
@@ -964,7 +993,13 @@ int direct_slab_run(nns_handle *h, double *u, double *v, double *p, int nsteps, 
         dslab_update_kernel<<<grd, blk, 0, st>>>(g, uc, vc, pc, un, vn, h->d_nonfinite, h->params.flags & NNS_FLAG_CHECK_FINITE);
         h->launches += 2;
         if ((rc = apply_bc_list(h, g, 0, un, st)) || (rc = apply_bc_list(h, g, 1, vn, st))) return rc;
-        if ((rc = exchange_rows(h, S, un, st)) || (rc = exchange_rows(h, S, vn, st))) return rc;
+        if (overlap) {       // one communicator, one stream for its operations
+            NNS_CUDA(cudaEventRecord(S->ev_edge, st));
+            NNS_CUDA(cudaStreamWaitEvent(S->st_x, S->ev_edge, 0));
+            if ((rc = exchange_rows(h, S, un, S->st_x)) || (rc = exchange_rows(h, S, vn, S->st_x))) return rc;
+            NNS_CUDA(cudaEventRecord(S->ev_xdone, S->st_x));
+            NNS_CUDA(cudaStreamWaitEvent(st, S->ev_xdone, 0));
+        } else if ((rc = exchange_rows(h, S, un, st)) || (rc = exchange_rows(h, S, vn, st))) return rc;
         double *t;
         t = uc; uc = un; un = t;
         t = vc; vc = vn; vn = t;
