@@ -39,18 +39,23 @@ struct GemmTable {
     int n;
 };
 
-constexpr int TM = 64, TN = 64, TK = 16;
-constexpr int SA = TK + 4, SB = TN + 4;     // shared-memory strides (doubles): conflict-free fragment loads (stride = 4 mod 16)
+constexpr int TK = 16;
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// 64 x 64 tile per CTA, 8 warps: warp (wy, wx) of a 2 x 4 grid computes 32 x 16 = 4 x 2 DMMA tiles of 8 x 8.
+// TM x TN tile per CTA, 8 warps: warp (wy, wx) of a 2 x 4 grid computes (TM / 2) x (TN / 4) = WM x WN DMMA tiles of 8 x 8
+// (64 x 64: 4 x 2 tiles per warp, for ensembles; 32 x 32 and 16 x 32 for a few simulations, whose 125 x 125 products would
+// otherwise occupy 4 CTAs each: 0.177 -> 0.117 -> 0.111 ms/step for a single N = 127 simulation).
 // m8n8k4 fragments: lane l holds A[l / 4][l % 4], B[l % 4][l / 4], C[l / 4][2 (l % 4) + {0, 1}].
 // The next k-slab travels global -> registers while the current one is multiplied out of shared memory.
+template <int TM, int TN>
 __global__ void __launch_bounds__(256) spectral_gemm_kernel(const GemmTable tab, int batch) {
+    constexpr int SA = TK + 4, SB = TN + 4;     // shared-memory strides (doubles): conflict-free fragment loads (stride = 4 mod 16)
+    constexpr int WM = TM / 16, WN = TN / 32;   // DMMA tiles per warp
+    constexpr int QA = TM * TK / 256, QB = TN * TK / 256;       // elements per thread and slab
     const int gi = blockIdx.z / batch, b = blockIdx.z - gi * batch;
     const GemmDesc &d = tab.g[gi];
     const int row0 = blockIdx.y * TM, col0 = blockIdx.x * TN;
@@ -61,33 +66,33 @@ __global__ void __launch_bounds__(256) spectral_gemm_kernel(const GemmTable tab,
     double *C = d.C + (long long)b * d.sC;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wy = warp >> 2, wx = warp & 3;
     const int fr = lane >> 2, fk = lane & 3;
-    double acc[4][2][2];
+    double acc[WM][WN][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < WM; ++i)
 #pragma unroll
-        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    double ra[4], rb[4];
-    // A slab: 64 rows x 16 k (thread: row tid / 4, k = 4 (tid % 4) .. +3); B slab: 16 k x 64 cols
+        for (int j = 0; j < WN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    double ra[QA], rb[QB];
+    // A slab: TM rows x 16 k (thread: QA consecutive k of one row); B slab: 16 k x TN cols
     auto gload = [&](int k0) {
         {
-            const int r = tid >> 2, kk = (tid & 3) * 4, gr = row0 + r;
+            const int r = tid / (TK / QA), kk = (tid % (TK / QA)) * QA, gr = row0 + r;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < QA; ++q) {
                 const int gk = k0 + kk + q;
                 ra[q] = (gr < d.m && gk < d.k) ? A[(long long)gr * d.lda + gk] : 0.0;
             }
         }
-        if (d.transB) {       // B stored n x k: thread reads 4 consecutive k of one column
-            const int c = tid >> 2, kk = (tid & 3) * 4, gc = col0 + c;
+        if (d.transB) {       // B stored n x k: thread reads QB consecutive k of one column
+            const int c = tid / (TK / QB), kk = (tid % (TK / QB)) * QB, gc = col0 + c;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < QB; ++q) {
                 const int gk = k0 + kk + q;
                 rb[q] = (gc < d.n && gk < d.k) ? B[(long long)gc * d.ldb + gk] : 0.0;
             }
-        } else {              // B stored k x n: thread reads 4 consecutive columns of one k
-            const int kk = tid >> 4, c = (tid & 15) * 4, gk = k0 + kk;
+        } else {              // B stored k x n: thread reads QB consecutive columns of one k
+            const int kk = tid / (TN / QB), c = (tid % (TN / QB)) * QB, gk = k0 + kk;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < QB; ++q) {
                 const int gc = col0 + c + q;
                 rb[q] = (gc < d.n && gk < d.k) ? B[(long long)gk * d.ldb + gc] : 0.0;
             }
@@ -95,18 +100,18 @@ __global__ void __launch_bounds__(256) spectral_gemm_kernel(const GemmTable tab,
     };
     auto sstore = [&]() {
         {
-            const int r = tid >> 2, kk = (tid & 3) * 4;
+            const int r = tid / (TK / QA), kk = (tid % (TK / QA)) * QA;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) As[r * SA + kk + q] = ra[q];
+            for (int q = 0; q < QA; ++q) As[r * SA + kk + q] = ra[q];
         }
         if (d.transB) {
-            const int c = tid >> 2, kk = (tid & 3) * 4;
+            const int c = tid / (TK / QB), kk = (tid % (TK / QB)) * QB;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) Bs[(kk + q) * SB + c] = rb[q];
+            for (int q = 0; q < QB; ++q) Bs[(kk + q) * SB + c] = rb[q];
         } else {
-            const int kk = tid >> 4, c = (tid & 15) * 4;
+            const int kk = tid / (TN / QB), c = (tid % (TN / QB)) * QB;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) Bs[kk * SB + c + q] = rb[q];
+            for (int q = 0; q < QB; ++q) Bs[kk * SB + c + q] = rb[q];
         }
     };
     gload(0);
@@ -117,24 +122,24 @@ __global__ void __launch_bounds__(256) spectral_gemm_kernel(const GemmTable tab,
         if (k0 + TK < d.k) gload(k0 + TK);
 #pragma unroll
         for (int k4 = 0; k4 < TK; k4 += 4) {
-            double af[4], bf[2];
+            double af[WM], bf[WN];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) af[i] = As[(wy * 32 + i * 8 + fr) * SA + k4 + fk];
+            for (int i = 0; i < WM; ++i) af[i] = As[(wy * (TM / 2) + i * 8 + fr) * SA + k4 + fk];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) bf[j] = Bs[(k4 + fk) * SB + wx * 16 + j * 8 + fr];
+            for (int j = 0; j < WN; ++j) bf[j] = Bs[(k4 + fk) * SB + wx * (TN / 4) + j * 8 + fr];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < WM; ++i)
 #pragma unroll
-                for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < WN; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < WM; ++i)
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
+        for (int j = 0; j < WN; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int gr = row0 + wy * 32 + i * 8 + fr, gc = col0 + wx * 16 + j * 8 + 2 * fk + e;
+                const int gr = row0 + wy * (TM / 2) + i * 8 + fr, gc = col0 + wx * (TN / 4) + j * 8 + 2 * fk + e;
                 if (gr < d.m && gc < d.n) {
                     double v = acc[i][j][e];
                     if (d.epi == 1) v = v / (d.e0 + d.e1 * d.lx[gr] + d.e2 * d.ly[gc]);
@@ -265,8 +270,20 @@ struct SpectralPlan {
 static int run_table(nns_handle *h, GemmTable &t, int batch, cudaStream_t st) {
     int mm = 0, nn = 0;
     for (int i = 0; i < t.n; ++i) { mm = t.g[i].m > mm ? t.g[i].m : mm; nn = t.g[i].n > nn ? t.g[i].n : nn; }
-    dim3 grid((nn + TN - 1) / TN, (mm + TM - 1) / TM, t.n * batch);
-    spectral_gemm_kernel<<<grid, 256, 0, st>>>(t, batch);
+    // few products in the launch (a single simulation): smaller tiles, 4 or 8 times the CTAs
+    const long ctas64 = (long)((nn + 63) / 64) * ((mm + 63) / 64) * t.n * batch;
+    const char *tile = getenv("NNS_SPECTRAL_TILE");          // experiments: 32 / 64
+    const bool small = tile ? atoi(tile) == 32 : ctas64 < 2L * h->sm_count;
+    if (tile ? atoi(tile) == 16 : 2 * ctas64 < h->sm_count) {
+        dim3 grid((nn + 31) / 32, (mm + 15) / 16, t.n * batch);
+        spectral_gemm_kernel<16, 32><<<grid, 256, 0, st>>>(t, batch);
+    } else if (small) {
+        dim3 grid((nn + 31) / 32, (mm + 31) / 32, t.n * batch);
+        spectral_gemm_kernel<32, 32><<<grid, 256, 0, st>>>(t, batch);
+    } else {
+        dim3 grid((nn + 63) / 64, (mm + 63) / 64, t.n * batch);
+        spectral_gemm_kernel<64, 64><<<grid, 256, 0, st>>>(t, batch);
+    }
     NNS_CUDA(cudaGetLastError());
     h->launches += 1;
     return NNS_OK;
