@@ -39,7 +39,6 @@ struct GemmTable {
     int n;
 };
 
-constexpr int TK = 16;
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
@@ -51,7 +50,7 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 // otherwise occupy 4 CTAs each: 0.177 -> 0.117 -> 0.111 ms/step for a single N = 127 simulation).
 // m8n8k4 fragments: lane l holds A[l / 4][l % 4], B[l % 4][l / 4], C[l / 4][2 (l % 4) + {0, 1}].
 // The next k-slab travels global -> registers while the current one is multiplied out of shared memory.
-template <int TM, int TN>
+template <int TM, int TN, int TK>
 __global__ void __launch_bounds__(256) spectral_gemm_kernel(const GemmTable tab, int batch) {
     constexpr int SA = TK + 4, SB = TN + 4;     // shared-memory strides (doubles): conflict-free fragment loads (stride = 4 mod 16)
     constexpr int WM = TM / 16, WN = TN / 32;   // DMMA tiles per warp
@@ -292,6 +291,9 @@ struct SpectralPlan {
     long long gnodes;
 };
 
+#ifndef NNS_SPECTRAL_TK_SMALL
+#define NNS_SPECTRAL_TK_SMALL 32      // k-slab of the 16 x 32-tile instance (a single simulation: fewer barriers per product)
+#endif
 static int run_table(nns_handle *h, GemmTable &t, int batch, cudaStream_t st) {
     int mm = 0, nn = 0;
     for (int i = 0; i < t.n; ++i) { mm = t.g[i].m > mm ? t.g[i].m : mm; nn = t.g[i].n > nn ? t.g[i].n : nn; }
@@ -301,13 +303,13 @@ static int run_table(nns_handle *h, GemmTable &t, int batch, cudaStream_t st) {
     const bool small = tile ? atoi(tile) == 32 : ctas64 < 2L * h->sm_count;
     if (tile ? atoi(tile) == 16 : 2 * ctas64 < h->sm_count) {
         dim3 grid((nn + 31) / 32, (mm + 15) / 16, t.n * batch);
-        spectral_gemm_kernel<16, 32><<<grid, 256, 0, st>>>(t, batch);
+        spectral_gemm_kernel<16, 32, NNS_SPECTRAL_TK_SMALL><<<grid, 256, 0, st>>>(t, batch);
     } else if (small) {
         dim3 grid((nn + 31) / 32, (mm + 31) / 32, t.n * batch);
-        spectral_gemm_kernel<32, 32><<<grid, 256, 0, st>>>(t, batch);
+        spectral_gemm_kernel<32, 32, 16><<<grid, 256, 0, st>>>(t, batch);
     } else {
         dim3 grid((nn + 63) / 64, (mm + 63) / 64, t.n * batch);
-        spectral_gemm_kernel<64, 64><<<grid, 256, 0, st>>>(t, batch);
+        spectral_gemm_kernel<64, 64, 16><<<grid, 256, 0, st>>>(t, batch);
     }
     NNS_CUDA(cudaGetLastError());
     h->launches += 1;
