@@ -291,6 +291,9 @@ struct SpectralPlan {
     long long gnodes;
 };
 
+#ifndef NNS_SPECTRAL_TK_LARGE
+#define NNS_SPECTRAL_TK_LARGE 16
+#endif
 #ifndef NNS_SPECTRAL_TK_SMALL
 #define NNS_SPECTRAL_TK_SMALL 32      // k-slab of the 16 x 32-tile instance (a single simulation: fewer barriers per product)
 #endif
@@ -309,7 +312,7 @@ static int run_table(nns_handle *h, GemmTable &t, int batch, cudaStream_t st) {
         spectral_gemm_kernel<32, 32, 16><<<grid, 256, 0, st>>>(t, batch);
     } else {
         dim3 grid((nn + 63) / 64, (mm + 63) / 64, t.n * batch);
-        spectral_gemm_kernel<64, 64, 16><<<grid, 256, 0, st>>>(t, batch);
+        spectral_gemm_kernel<64, 64, NNS_SPECTRAL_TK_LARGE><<<grid, 256, 0, st>>>(t, batch);
     }
     NNS_CUDA(cudaGetLastError());
     h->launches += 1;
