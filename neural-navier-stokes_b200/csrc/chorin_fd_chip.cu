@@ -33,6 +33,14 @@
 
 namespace nns {
 
+#ifdef NNS_CHIP_PROF          // experiments: phase cycle counters of CTA 0 (thread 0), printed at the end of the launch
+__device__ long long g_cprof[8];
+#define CPF(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long now_ = clock64(); g_cprof[k] += now_ - g_cprof[7]; g_cprof[7] = now_; } } while (0)
+#else
+#define CPF(k)
+#endif
+
+
 struct BlockDesc {      // REG path: one per thread, built on the host (chorin_chip_plan)
     short r0, c0;       // first row / column of the block (interior starts at 1)
     short nN, nS, nW, nE;   // thread ids of the neighbouring blocks, -1 = physical boundary / none
@@ -315,6 +323,7 @@ struct SplitSor {
         for (int i = warp; i < nx; i += nwarps)
             for (int j = lane; j < ny; j += 32) pg[(size_t)i * ny + j] = Ps[split_off(i, j, PH, HS)];
         __syncthreads();
+        CPF(3);
         return need;
     }
 };
@@ -497,6 +506,7 @@ struct RegSor {
                     P[li][lj] = (owner && i < nx && j < ny) ? pg[(size_t)i * ny + j] : 0.0;
                 }
         };
+        CPF(0);
         scatter([&](int i, int j) { return pg[(size_t)i * ny + j]; });
         auto pval = [&](int i, int j) { return (i >= 0 && i < nx && j >= 0 && j < ny) ? pg[(size_t)i * ny + j] : 0.0; };
         if (owner) {
@@ -523,6 +533,7 @@ struct RegSor {
             }
             return c;
         });
+        CPF(1);
         int need = 0;
         if (cap > 0) {
             unsigned long long mask = 0ull;
@@ -536,6 +547,7 @@ struct RegSor {
                                                      cols_live, need, k, dummy);
             }
         }
+        CPF(2);
         // registers -> own chunks -> coalesced stores of the interior of p
         __syncthreads();                      // C' (and, with cap == 0, its scatter) is dead from here on
         {
@@ -598,6 +610,9 @@ __device__ __forceinline__ void chorin_chip_body(const ChipArgs &a) {
     int cur = 0, prev = 1, nxt = 2;
     double *pg = a.p + (size_t)b * N;
 
+#ifdef NNS_CHIP_PROF
+    if (blockIdx.x == 0 && threadIdx.x == 0) g_cprof[7] = clock64();
+#endif
     for (int n = 0; n < a.nsteps; ++n) {
         const double *uc = a.bufU[cur] + (size_t)b * N, *vc = a.bufV[cur] + (size_t)b * N;
         const double *up = a.bufU[prev] + (size_t)b * N, *vp = a.bufV[prev] + (size_t)b * N;
@@ -620,9 +635,17 @@ __device__ __forceinline__ void chorin_chip_body(const ChipArgs &a) {
 
         if (a.phases & 6) phase_finish(a, pg, un, vn, bcval, ((size_t)b * a.nsteps_total + (a.step0 + n)) * N);
         __syncthreads();
+        CPF(4);
         const int t = prev; prev = cur; cur = nxt; nxt = t;
     }
 
+#ifdef NNS_CHIP_PROF
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.nsteps >= 100) {
+        printf("chip prof (cycles/step): predictor %lld | sor setup %lld | wavefront+reduce %lld | store p %lld | finish %lld\n",
+               g_cprof[0] / a.nsteps, g_cprof[1] / a.nsteps, g_cprof[2] / a.nsteps, g_cprof[3] / a.nsteps, g_cprof[4] / a.nsteps);
+        for (int k = 0; k < 7; ++k) g_cprof[k] = 0;
+    }
+#endif
     if (a.fixup && cur != 0) {
         // final roles -> caller's buffers: buffer 0 must hold step n, buffer 1 step n-1
         double *U0 = a.bufU[0] + (size_t)b * N, *U1 = a.bufU[1] + (size_t)b * N, *U2 = a.bufU[2] + (size_t)b * N;
