@@ -576,7 +576,7 @@ struct RegSor {
 
 // ================================== the fused step kernel =======================================
 // MODE 0: SPLIT with C' in smem, 1: SPLIT with C' in global, 2: REG<2,4,512>, 3: REG<7,6,384>,
-// 4: REG<2,4,256>
+// 4: REG<2,4,256>, 5: REG<3,3,256> (grids whose interior is tiled exactly by 3 x 3 blocks)
 template <int MODE>
 __device__ __forceinline__ void chorin_chip_body(const ChipArgs &a) {
     extern __shared__ double smem[];
@@ -592,6 +592,7 @@ __device__ __forceinline__ void chorin_chip_body(const ChipArgs &a) {
     else if constexpr (MODE == 1) used = (size_t)2 * a.HS;
     else if constexpr (MODE == 2) used = RegSor<2, 4, 512>::SMEM_DOUBLES;
     else if constexpr (MODE == 4) used = RegSor<2, 4, 256>::SMEM_DOUBLES;
+    else if constexpr (MODE == 5) used = RegSor<3, 3, 256>::SMEM_DOUBLES;
     else used = RegSor<7, 6, 384>::SMEM_DOUBLES;
     double *aux = smem + used;                             // 2*nx doubles (Thomas coefficients)
     int *viol = reinterpret_cast<int *>(aux + 2 * nx);     // max(0, nit-65) ints
@@ -629,6 +630,7 @@ __device__ __forceinline__ void chorin_chip_body(const ChipArgs &a) {
             else if constexpr (MODE == 1) need = SplitSor::run<false>(a, smem, un, vn, pg, k, cap, viol, &s_mask, &s_need);
             else if constexpr (MODE == 2) need = RegSor<2, 4, 512>::run(a, smem, un, vn, pg, k, cap, viol, &s_mask, &s_need);
             else if constexpr (MODE == 4) need = RegSor<2, 4, 256>::run(a, smem, un, vn, pg, k, cap, viol, &s_mask, &s_need);
+            else if constexpr (MODE == 5) need = RegSor<3, 3, 256>::run(a, smem, un, vn, pg, k, cap, viol, &s_mask, &s_need);
             else need = RegSor<7, 6, 384>::run(a, smem, un, vn, pg, k, cap, viol, &s_mask, &s_need);
             if (a.sweeps && tid == 0) a.sweeps[(size_t)(a.step0 + n) * a.g.batch + b] = need;
         }
@@ -728,6 +730,7 @@ static int forced_mode() {
     if (e && !strcmp(e, "split")) return 0;
     if (e && !strcmp(e, "reg24")) return 2;
     if (e && !strcmp(e, "reg76")) return 3;
+    if (e && !strcmp(e, "reg33")) return 5;
     return -1;
 }
 
@@ -737,6 +740,8 @@ ChipPlan chorin_chip_plan(const nns_handle *h) {
     const int force = forced_mode();
     if (force != 0 && h->g.nit <= 65) {      // REG keeps the per-sweep exit flags in one 64-bit mask
         // doubles per thread: C' (2*NCH) + halo slots: RegSor<2,4>: 8 + 12; RegSor<7,6>: 42 + 26
+        // 3 x 3 blocks when they tile the interior exactly (no ragged blocks: e.g. 41 x 41 = 13 x 13 blocks of 3 x 3)
+        if ((force < 0 || force == 5) && (nx - 2) % 3 == 0 && (ny - 2) % 3 == 0 && plan_reg(h, 3, 3, 256, 10 + 12, pl)) { pl.mode = 5; return pl; }
         if ((force < 0 || force == 2) && plan_reg(h, 2, 4, 256, 8 + 12, pl)) { pl.mode = 4; return pl; }
         if ((force < 0 || force == 2) && plan_reg(h, 2, 4, 512, 8 + 12, pl)) { pl.mode = 2; return pl; }
         if ((force < 0 || force == 3) && plan_reg(h, 7, 6, 384, 42 + 26, pl)) { pl.mode = 3; return pl; }
@@ -797,6 +802,7 @@ int chorin_chip_launch(nns_handle *h, ChipArgs &a, cudaStream_t st, int m0, int 
         case 1: rc = launch_mode<1, 1024>(pl, a, count, st); break;
         case 2: rc = launch_mode<2, 512>(pl, a, count, st); break;
         case 4: rc = launch_mode<4, 256>(pl, a, count, st); break;
+        case 5: rc = launch_mode<5, 256>(pl, a, count, st); break;
         default:
             NNS_CUDA(cudaFuncSetAttribute(chorin_chip_kernel_reg76, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)pl.smem_bytes));
