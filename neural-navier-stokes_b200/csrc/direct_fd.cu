@@ -59,9 +59,35 @@ __device__ __forceinline__ void cta_apply_bc_smem(double *A, int nx, int ny, int
     }
 }
 
+// The same walk with the list staged in shared memory (vals[k], code[k] = side | type << 8): inside the sweep loop a
+// per-member value is otherwise a global load, the side / type an indexed parameter load, in front of every entry of every sweep.
+__device__ __forceinline__ void cta_apply_bc_smem_staged(double *A, int nx, int ny, int pitch, int nent, const double *vals,
+                                                         const int *code, double dx, double dy) {
+    for (int k = 0; k < nent; ++k) {
+        const double g = vals[k];
+        const int side = code[k] & 0xff;
+        const bool neu = (code[k] >> 8) == NNS_BC_NEUMANN;
+        if (side == NNS_SIDE_LEFT || side == NNS_SIDE_RIGHT) {
+            const int i = side == NNS_SIDE_LEFT ? 0 : nx - 1, in = side == NNS_SIDE_LEFT ? 1 : nx - 2;
+            const double sg = side == NNS_SIDE_LEFT ? -dx : dx;
+            for (int j = threadIdx.x; j < ny; j += blockDim.x)
+                A[i * pitch + j] = neu ? A[in * pitch + j] + sg * g : g;
+        } else {
+            const int j = side == NNS_SIDE_BOTTOM ? 0 : ny - 1, jn = side == NNS_SIDE_BOTTOM ? 1 : ny - 2;
+            const double sg = side == NNS_SIDE_BOTTOM ? -dy : dy;
+            for (int i = threadIdx.x; i < nx; i += blockDim.x)
+                A[i * pitch + j] = neu ? A[i * pitch + jn] + sg * g : g;
+        }
+        __syncthreads();
+    }
+}
+
 // ---- chip path -------------------------------------------------------------------------
 // smem: P0, P1 (ping-pong), Bs: 3 * nx * pitch doubles.
-__global__ void __launch_bounds__(1024, 1) direct_chip_kernel(const DirectArgs a) {
+// (NTMAX: the launch's thread count bounds the registers per thread -- 64 at 1024 threads, where ptxas re-reads loop
+// invariants from the constant bank in every iteration; smaller grids run with 512 or 256 threads and 128 / 255 registers)
+template <int NTMAX>
+__global__ void __launch_bounds__(NTMAX, 1) direct_chip_kernel(const DirectArgs a) {
     extern __shared__ double smem[];
     const int nx = a.g.nx, ny = a.g.ny, pitch = ny | 1;
     const size_t N = (size_t)nx * ny;
@@ -80,6 +106,9 @@ __global__ void __launch_bounds__(1024, 1) direct_chip_kernel(const DirectArgs a
     const bool per = a.flags & NNS_FLAG_PERIODIC_X;
     const double fdt = per ? a.force_x * dt : 0.0;
 
+    __shared__ double s_pval[NNS_MAX_BC];
+    __shared__ int s_pcode[NNS_MAX_BC];
+    if (tid < a.pbc.n) { s_pval[tid] = bcval ? bcval[a.pbc.slot[tid]] : a.pbc.value[tid]; s_pcode[tid] = a.pbc.side[tid] | (a.pbc.type[tid] << 8); }
     for (int i = warp; i < nx; i += nwarps)
         for (int j = lane; j < ny; j += 32) P0[i * pitch + j] = pg[(size_t)i * ny + j];
     __syncthreads();
@@ -115,7 +144,7 @@ __global__ void __launch_bounds__(1024, 1) direct_chip_kernel(const DirectArgs a
                     Pn[q] = r;
                 }
             __syncthreads();
-            cta_apply_bc_smem(Pn, nx, ny, pitch, a.pbc, bcval, dx, dy);
+            cta_apply_bc_smem_staged(Pn, nx, ny, pitch, a.pbc.n, s_pval, s_pcode, dx, dy);
             double *t = Pc; Pc = Pn; Pn = t;
         }
         // velocity update (direct_fd:98-118) into the partner buffers, then u/v BCs (:121-125)
@@ -730,8 +759,9 @@ int direct_run(nns_handle *h, double *u, double *v, double *p, int nsteps, doubl
         a.traj_u = tu; a.traj_v = tv; a.traj_p = tp; a.nonfinite = h->d_nonfinite;
         const long cells = (long)g.nx * g.ny;
         const int threads = cells >= 8192 ? 1024 : cells >= 1024 ? 512 : 256;
-        NNS_CUDA(cudaFuncSetAttribute(direct_chip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        direct_chip_kernel<<<g.batch, threads, smem, st>>>(a);
+        auto kern = threads == 1024 ? direct_chip_kernel<1024> : threads == 512 ? direct_chip_kernel<512> : direct_chip_kernel<256>;
+        NNS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<g.batch, threads, smem, st>>>(a);
         NNS_CUDA(cudaGetLastError());
         h->launches += 1;
         return NNS_OK;
