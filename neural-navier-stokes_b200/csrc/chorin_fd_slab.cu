@@ -868,18 +868,12 @@ __device__ __forceinline__ double dslab_jac(const double *__restrict__ pc, const
 
 // rows: ra >= 0: the two rows ra, rb (blockIdx.y = 0 / 1: the slab's edge rows, swept first so that their exchange runs
 // under the interior sweep); else the rows g.row0 + roff + blockIdx.y
-__global__ void dslab_jacobi_bc_kernel(SlabGeom g, DirectBcPlan bc, const double *__restrict__ pc, const double *__restrict__ bs,
-                                       double *__restrict__ pn, int ra, int rb, int roff, int rend) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = ra >= 0 ? (blockIdx.y == 0 ? ra : rb) : g.row0 + roff + (int)blockIdx.y;
-    if (j >= g.ny || i >= (ra >= 0 ? g.row1 : rend)) return;
+__device__ __forceinline__ double dslab_cell(const SlabGeom &g, const DirectBcPlan &bc, const double *__restrict__ pc,
+                                             const double *__restrict__ bs, int i, int j, double cx, double cy) {
     const size_t q = g.v.at(i, j);
     const int ny = g.ny, nx = g.nx;
-    const double dx2 = g.dx * g.dx, dy2 = g.dy * g.dy;
-    const double rden = 1.0 / (2.0 * (dx2 + dy2));
-    const double cx = dy2 * rden, cy = dx2 * rden;
     const bool rowe = i == 0 || i == nx - 1, cole = j == 0 || j == ny - 1;
-    if (!rowe && !cole) { pn[q] = dslab_jac(pc, bs, q, ny, cx, cy); return; }
+    if (!rowe && !cole) return dslab_jac(pc, bs, q, ny, cx, cy);
     const int rside = i == 0 ? NNS_SIDE_LEFT : NNS_SIDE_RIGHT, cside = j == 0 ? NNS_SIDE_BOTTOM : NNS_SIDE_TOP;
     const int ii = i == 0 ? 1 : nx - 2, ji = j == 0 ? 1 : ny - 2;          // the adjacent interior row / column
     const double rsg = i == 0 ? -g.dx : g.dx, csg = j == 0 ? -g.dy : g.dy;
@@ -897,7 +891,38 @@ __global__ void dslab_jacobi_bc_kernel(SlabGeom g, DirectBcPlan bc, const double
             else if (bc.side[k] == cside) { t_adj = bc.neu[k] ? a11 + csg * gv : gv; r = bc.neu[k] ? t_row + csg * gv : gv; }
         }
     }
-    pn[q] = r;
+    return r;
+}
+
+// VEC: a thread updates the two cells j = 2t, 2t + 1 with 128-bit loads / stores (ny even: rows are 16-byte aligned)
+template <bool VEC>
+__global__ void __launch_bounds__(128) dslab_jacobi_bc_kernel(SlabGeom g, DirectBcPlan bc, const double *__restrict__ pc,
+                                                              const double *__restrict__ bs, double *__restrict__ pn, int ra, int rb,
+                                                              int roff, int rend) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, j = VEC ? 2 * t : t;
+    const int i = ra >= 0 ? (blockIdx.y == 0 ? ra : rb) : g.row0 + roff + (int)blockIdx.y;
+    if (j >= g.ny || i >= (ra >= 0 ? g.row1 : rend)) return;
+    const int ny = g.ny, nx = g.nx;
+    const double dx2 = g.dx * g.dx, dy2 = g.dy * g.dy;
+    const double rden = 1.0 / (2.0 * (dx2 + dy2));
+    const double cx = dy2 * rden, cy = dx2 * rden;
+    if (VEC) {
+        const size_t q = g.v.at(i, j);
+        if (i > 0 && i < nx - 1 && j >= 2 && j + 1 <= ny - 2) {          // both cells interior: the same expression as dslab_jac
+            const double2 C = *reinterpret_cast<const double2 *>(pc + q), Nn = *reinterpret_cast<const double2 *>(pc + q - ny);
+            const double2 S = *reinterpret_cast<const double2 *>(pc + q + ny), B = *reinterpret_cast<const double2 *>(bs + q);
+            const double W = pc[q - 1], E = pc[q + 2];
+            double2 r;
+            r.x = (C.y + W) * cx + (S.x + Nn.x) * cy - B.x;
+            r.y = (E + C.x) * cx + (S.y + Nn.y) * cy - B.y;
+            *reinterpret_cast<double2 *>(pn + q) = r;
+        } else {
+            pn[q] = dslab_cell(g, bc, pc, bs, i, j, cx, cy);
+            if (j + 1 < ny) pn[q + 1] = dslab_cell(g, bc, pc, bs, i, j + 1, cx, cy);
+        }
+    } else {
+        pn[g.v.at(i, j)] = dslab_cell(g, bc, pc, bs, i, j, cx, cy);
+    }
 }
 
 __global__ void dslab_update_kernel(SlabGeom g, const double *__restrict__ uo, const double *__restrict__ vo,
@@ -951,6 +976,8 @@ int direct_slab_run(nns_handle *h, double *u, double *v, double *p, int nsteps, 
             plan.kind[L.side[k]] = plan.neu[k] ? 2 : 1; plan.g[L.side[k]] = L.value[k];
         }
     }
+    const bool vec = G.ny % 2 == 0 && !getenv("NNS_DSLAB_SCALAR");        // two cells per thread, 128-bit accesses
+    const unsigned grdv = (unsigned)((G.ny / 2 + 127) / 128);
     const char *bcm = getenv("NNS_DSLAB_BC");
     const bool owns_top = S->row0 == 0, owns_bot = S->row0 + S->nrows == G.nx;
     const bool fused_bc = !(bcm && strcmp(bcm, "list") == 0) && G.nx >= 4 && G.ny >= 3 &&
@@ -968,19 +995,22 @@ int direct_slab_run(nns_handle *h, double *u, double *v, double *p, int nsteps, 
         for (int s = 0; s < G.nit; ++s) {
             if (fused_bc && overlap) {
                 // edge rows, their exchange on the second stream, the interior rows meanwhile on the first
-                dslab_jacobi_bc_kernel<<<dim3(grd.x, 2), blk, 0, st>>>(g, plan, pc, b, pn, g.row0, g.row1 - 1, 0, 0);
+                if (vec) dslab_jacobi_bc_kernel<true><<<dim3(grdv, 2), blk, 0, st>>>(g, plan, pc, b, pn, g.row0, g.row1 - 1, 0, 0);
+                else dslab_jacobi_bc_kernel<false><<<dim3(grd.x, 2), blk, 0, st>>>(g, plan, pc, b, pn, g.row0, g.row1 - 1, 0, 0);
                 NNS_CUDA(cudaEventRecord(S->ev_edge, st));
                 NNS_CUDA(cudaStreamWaitEvent(S->st_x, S->ev_edge, 0));
                 if ((rc = exchange_rows(h, S, pn, S->st_x))) return rc;
                 NNS_CUDA(cudaEventRecord(S->ev_xdone, S->st_x));
-                dslab_jacobi_bc_kernel<<<dim3(grd.x, S->nrows - 2), blk, 0, st>>>(g, plan, pc, b, pn, -1, -1, 1, g.row1 - 1);
+                if (vec) dslab_jacobi_bc_kernel<true><<<dim3(grdv, S->nrows - 2), blk, 0, st>>>(g, plan, pc, b, pn, -1, -1, 1, g.row1 - 1);
+                else dslab_jacobi_bc_kernel<false><<<dim3(grd.x, S->nrows - 2), blk, 0, st>>>(g, plan, pc, b, pn, -1, -1, 1, g.row1 - 1);
                 NNS_CUDA(cudaStreamWaitEvent(st, S->ev_xdone, 0));
                 h->launches += 2;
                 double *t = pc; pc = pn; pn = t;
                 continue;
             }
             if (fused_bc) {
-                dslab_jacobi_bc_kernel<<<grd, blk, 0, st>>>(g, plan, pc, b, pn, -1, -1, 0, g.row1);
+                if (vec) dslab_jacobi_bc_kernel<true><<<dim3(grdv, grd.y), blk, 0, st>>>(g, plan, pc, b, pn, -1, -1, 0, g.row1);
+                else dslab_jacobi_bc_kernel<false><<<grd, blk, 0, st>>>(g, plan, pc, b, pn, -1, -1, 0, g.row1);
                 h->launches += 1;
             } else {
                 dslab_jacobi_kernel<<<grd, blk, 0, st>>>(g, pc, b, pn);

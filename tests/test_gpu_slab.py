@@ -241,8 +241,12 @@ def test_direct_fd_slab_fused_bcs_equal_list_walk(oracle_fd, monkeypatch):
     u_bc, v_bc, p_bc = _bcs(nx, ny, "mixed")
     ic = smooth_ic(nx, ny, 5, amp=0.1)
     out = {}
-    for mode in ("fused", "list"):
-        monkeypatch.setenv("NNS_DSLAB_BC", mode)
+    for mode in ("fused", "fused_scalar", "list"):
+        monkeypatch.setenv("NNS_DSLAB_BC", mode.split("_")[0])
+        if mode == "fused_scalar":
+            monkeypatch.setenv("NNS_DSLAB_SCALAR", "1")       # one cell per thread instead of two with 128-bit accesses
+        else:
+            monkeypatch.delenv("NNS_DSLAB_SCALAR", raising=False)
         sl = SlabDirect(nx, ny, u_bc=u_bc, v_bc=v_bc, p_bc=p_bc, nit=7, dt=1e-4, rho=1.1, nu=0.05, rank=0, world=1)
         sl.set_state(*ic)
         sl.sync_halos()
@@ -253,6 +257,7 @@ def test_direct_fd_slab_fused_bcs_equal_list_walk(oracle_fd, monkeypatch):
     assert out["fused"][3] < out["list"][3]                   # the list walk really launches a kernel per entry
     for k in range(3):
         assert rel_l2(out["fused"][k], out["list"][k]) <= 1e-13
+        assert rel_l2(out["fused"][k], out["fused_scalar"][k]) <= 1e-13
     ou, ov, op = oracle_fd.direct_simulate(ic[0].copy(), ic[1].copy(), ic[2].copy(), _t(u_bc), _t(v_bc), _t(p_bc), nt=nsteps,
                                            nit=7, dt=1e-4, rho=1.1, nu=0.05)
     assert rel_l2(out["fused"][2], op[-1]) <= TOL and rel_l2(out["fused"][0], ou[-1]) <= TOL
